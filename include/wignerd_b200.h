@@ -1,0 +1,126 @@
+/* wignerd_b200.h -- C ABI of libwignerd_b200.so, the B200 (sm_100a) Wigner-d/D engine.
+ *
+ * This is the drop-in boundary for the hot path of jishnub/WignerD.jl v0.1.4.  The
+ * reference has no FFI of its own; its boundary is the Julia function API
+ * (src/WignerD.jl:9-12 exports, README.md:24,33 qualified names).  Every entry
+ * point below names the reference function it replaces; julia/WignerD.jl shows the
+ * `ccall` binding, wignerd/jl_b200/api.py the ctypes binding used by the tests.
+ *
+ * Conventions (identical to the reference):
+ *   - j is passed as twoj = 2j (int32), so integer and half-integer j share one
+ *     path -- the reference keys its own cache the same way, UInt(2j+1) (:164).
+ *     m, n likewise as twom = 2m, twon = 2n.
+ *   - a d matrix is N x N, N = 2j+1, COLUMN-MAJOR, element d[(j+m) + N*(j+n)] =
+ *     d^j_{m,n}(beta), rows/cols ascending from -j (README.md:18-22).  Batches are
+ *     nb such matrices back to back.  D matrices are the same with interleaved
+ *     (re, im) complex128 elements.
+ *   - Varshalovich phase convention, D^j_{mn} = exp(-i(m alpha + n gamma)) d^j_{mn}(beta)
+ *     (src/WignerD.jl:245, :339).
+ *   - no function throws or aborts across the boundary: each returns a wd_status and
+ *     leaves a message for wd_last_error() (thread-local).  The Julia shim maps the
+ *     codes back to the reference's exception types.
+ *   - `mem` says where the caller's angle/output buffers live: WD_MEM_HOST (pageable
+ *     or pinned host memory; the library stages through the device) or WD_MEM_DEVICE
+ *     (device pointers on the handle's GPU; nothing is copied, work is enqueued on the
+ *     handle's stream and the call returns without synchronising).
+ *   - there is NO CPU fallback: every compute entry point fails with WD_ERR_CUDA when no
+ *     sm_100-class device is usable.
+ */
+#ifndef WIGNERD_B200_H
+#define WIGNERD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wd_handle_s *wd_handle_t;
+
+typedef enum {
+    WD_OK = 0,
+    WD_ERR_ARGUMENT = 1, /* reference: ArgumentError (src/WignerD.jl:98,191-194) -- m/n outside -j..j */
+    WD_ERR_ASSERT = 2,   /* reference: AssertionError (:96-97,148-149,267) -- j < 0, bad sizes, null ptr */
+    WD_ERR_CUDA = 3,     /* CUDA runtime failure / no usable device */
+    WD_ERR_NOMEM = 4,    /* device or host allocation failed */
+    WD_ERR_UNSUPPORTED = 5
+} wd_status;
+
+/* beta::Real vs the special co-latitude types (src/WignerD.jl:14-46). */
+typedef enum {
+    WD_BETA_GENERIC = 0,
+    WD_BETA_NORTH = 1,  /* NorthPole(): beta = 0,    :218-222, :247-253 */
+    WD_BETA_SOUTH = 2,  /* SouthPole(): beta = pi,   :224-228, :255-264 */
+    WD_BETA_EQUATOR = 3 /* Equator():   beta = pi/2, :230-237 */
+} wd_beta_kind;
+
+enum { WD_MEM_HOST = 0, WD_MEM_DEVICE = 1 };
+
+/* ---- lifetime ------------------------------------------------------------------- */
+/* One handle = one GPU + one stream + the per-j eigenvector-table cache (replaces the
+ * per-Task JyEigenDict, src/WignerD.jl:137-138).  Calls on one handle are serialised by
+ * an internal mutex; use one handle per thread for concurrency (mirrors the per-Task
+ * cache that makes the reference safe under Threads.@threads). */
+int wd_create(int device, wd_handle_t *out);
+int wd_destroy(wd_handle_t h);
+const char *wd_last_error(void);
+int wd_abi_version(void);
+/* enqueue on a caller-owned cudaStream_t (0/NULL = the handle's own stream) */
+int wd_set_stream(wd_handle_t h, void *cuda_stream);
+int wd_synchronize(wd_handle_t h);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t wd_launch_count(wd_handle_t h);
+/* drop the cached per-j tables (the reference never frees its Dict) */
+int wd_cache_clear(wd_handle_t h);
+
+/* ---- spectral setup: replaces coeffi + eigen! + cache, src/WignerD.jl:145-185 ------ */
+/* Build (or find cached) the tables for every 2j in the list, in ONE batched launch of
+ * the tridiagonal eigensolver.  Implicitly called by everything below. */
+int wd_prepare(wd_handle_t h, const int32_t *twoj_list, int32_t nj);
+/* Real orthonormal eigenvectors u of J_x (J_y = S J_x S^dagger, S = diag((-i)^m)):
+ * u_out is N x N column-major on the HOST, u_out[(j+m) + N*k] = u[m, mu_k], mu_k = -j+k.
+ * <m|mu>_y = (-i)^m u[m,mu] up to a per-mu phase, which cancels in d.  Debug/parity. */
+int wd_eigvecs(wd_handle_t h, int32_t twoj, double *u_out);
+
+/* ---- matrices: replaces wignerd/wignerd! (:266-324) and wignerD/wignerD! (:335-357) -- */
+/* nb generic angles -> nb matrices (see layout above).  beta has nb entries. */
+int wd_d_batch(wd_handle_t h, int32_t twoj, const double *beta, int64_t nb, double *out, int mem);
+/* out has nb * N*N complex128 (2 doubles each). */
+int wd_D_batch(wd_handle_t h, int32_t twoj, const double *alpha, const double *beta,
+               const double *gamma, int64_t nb, double *out, int mem);
+/* Single matrix into HOST memory with the reference's in-place semantics (wignerd!):
+ * GENERIC/EQUATOR overwrite all N*N elements; NORTH writes only the diagonal and SOUTH only
+ * the anti-diagonal (:247-264 -- the caller supplies zeros, as wignerd does at :321). */
+int wd_d_matrix(wd_handle_t h, int32_t twoj, double beta, int beta_kind, double *d);
+/* wignerD!: d as above into the complex matrix, then every element *= cis(-(m alpha + n gamma)). */
+int wd_D_matrix(wd_handle_t h, int32_t twoj, double alpha, double beta, int beta_kind,
+                double gamma, double *D);
+/* Many j on one angle grid (spherical-harmonic rotation to lmax): for k in 0..nj-1 writes the
+ * nb matrices of twoj_list[k] at out + offsets[k] (offsets in doubles; blocks may alias when the
+ * caller ring-buffers).  beta: nb generic angles. */
+int wd_d_multi(wd_handle_t h, const int32_t *twoj_list, int32_t nj, const double *beta, int64_t nb,
+               double *out, const int64_t *offsets, int mem);
+
+/* ---- single elements: replaces WignerD.wignerdjmn (:214-237), wignerDjmn (:245) ------ */
+/* n tuples (twoj[t], twom[t], twon[t], beta[t]) -> out[t].  beta_kind applies to all tuples
+ * (beta is ignored for NORTH/SOUTH/EQUATOR).  Tuples with m or n outside -j..j (or of the
+ * wrong parity) make the call fail with WD_ERR_ARGUMENT (:190-193); out is then unspecified. */
+int wd_djmn_batch(wd_handle_t h, const int32_t *twoj, const int32_t *twom, const int32_t *twon,
+                  const double *beta, int64_t n, int beta_kind, double *out, int mem);
+/* out[t] = d * cis(-(alpha m + gamma n)), interleaved complex128. */
+int wd_Djmn_batch(wd_handle_t h, const int32_t *twoj, const int32_t *twom, const int32_t *twon,
+                  const double *alpha, const double *beta, const double *gamma, int64_t n,
+                  int beta_kind, double *out, int mem);
+
+/* ---- introspection for tests / benches ------------------------------------------- */
+/* kernel variant selection for wd_d_batch/wd_D_batch: 0 = auto, 1 = force the plain FP64-ALU
+ * kernel, 2 = force the DMMA kernel (fails if j does not fit). */
+int wd_set_variant(wd_handle_t h, int variant);
+/* FP64 micro-benchmarks used to calibrate the roofline (bench.py): returns TFLOP/s of a
+ * register-resident DMMA.8x8x4 (kind 0) or DFMA (kind 1) loop over the whole chip. */
+int wd_fp64_peak(wd_handle_t h, int kind, int iters, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WIGNERD_B200_H */

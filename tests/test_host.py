@@ -1,0 +1,118 @@
+"""Host logic and the C-ABI surface, without a GPU: the library loads, exports every symbol the header
+declares, maps errors, and the product refuses to compute without CUDA (no CPU fallback)."""
+import ctypes
+import os
+import re
+from fractions import Fraction as F
+from math import pi
+
+import numpy as np
+import pytest
+
+import wignerd.jl_b200 as w
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_builds_and_loads():
+    from wignerd.jl_b200 import build
+    path = build.build()
+    assert os.path.exists(path)
+    L = w.load_library()
+    assert L.wd_abi_version() == 1
+
+
+def test_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "wignerd_b200.h")).read()
+    declared = set(re.findall(r"\b(wd_[a-zA-Z0-9_]+)\s*\(", hdr))
+    assert declared == set(w.ABI_SYMBOLS), declared ^ set(w.ABI_SYMBOLS)
+    L = ctypes.CDLL(w.LIB_PATH)
+    for sym in declared:
+        assert hasattr(L, sym), sym
+
+
+def test_package_path_literal():
+    # the package is reachable as ./wignerd.jl_b200/ too (same directory)
+    assert os.path.samefile(os.path.join(ROOT, "wignerd.jl_b200"), os.path.join(ROOT, "wignerd", "jl_b200"))
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "wignerd")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert "libwignerd_ref" not in src, f
+
+
+@pytest.mark.skipif(_have_gpu(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_gpu():
+    with pytest.raises(w.CudaError):
+        w.Engine(0)
+    with pytest.raises(w.CudaError):
+        w.wignerd(1, 0.3)
+
+
+def test_null_and_bad_arguments_return_status_codes():
+    L = w.load_library()
+    assert L.wd_create(0, None) == 2                       # WD_ERR_ASSERT, never a crash
+    assert b"null" in L.wd_last_error()
+    assert L.wd_d_batch(None, 2, None, 1, None, 0) == 2
+    assert L.wd_prepare(None, None, 0) == 2
+    assert L.wd_launch_count(None) == 0
+    assert L.wd_destroy(None) == 0
+
+
+def test_twoj_of():
+    assert w.twoj_of(0) == 0 and w.twoj_of(1) == 2 and w.twoj_of(0.5) == 1 and w.twoj_of(F(7, 2)) == 7
+    assert w.twoj_of(1.5) == 3 and w.twoj_of(100) == 200
+    with pytest.raises(w.InexactError):
+        w.twoj_of(0.3)
+    with pytest.raises(AssertionError):
+        w.twoj_of(-1)
+
+
+def test_special_colatitudes():
+    # test/runtests.jl:23-43
+    assert float(w.Equator()) == pi / 2 and np.cos(w.NorthPole()) == 1 and np.sin(w.NorthPole()) == 0
+    assert float(w.SouthPole()) == pi and float(w.NorthPole()) == 0.0
+    assert w.Equator().kind == w.EQUATOR and w.NorthPole().kind == w.NORTH and w.SouthPole().kind == w.SOUTH
+    assert isinstance(w.Equator() * 2, float)              # promote_rule -> Float64
+    for a in range(-10, 11):                               # test/runtests.jl:17-22
+        for x in (a, F(a, 2)):
+            s, c = w._sincos(x, w.Equator())
+            assert abs(s - np.sin(float(x) * pi / 2)) < 1e-14 and abs(c - np.cos(float(x) * pi / 2)) < 1e-14
+
+
+def test_wigner_matrix_wrapper():
+    # test/runtests.jl:361-365
+    d = np.arange(4.0).reshape(2, 2)
+    wm = w._offsetmatrix(0.5, d)
+    assert wm.shape == (2, 2)
+    assert wm[-0.5, -0.5] == 0.0 and wm[F(1, 2), -0.5] == 2.0 and wm[0.5, 0.5] == 3.0
+    wm[0.5, -0.5] = 7.0
+    assert d[1, 0] == 7.0
+    with pytest.raises(AssertionError):
+        w._offsetmatrix(1, d)
+    with pytest.raises(IndexError):
+        wm[1, 0]
+
+
+@pytest.mark.parametrize("n,world", [(0, 1), (1, 4), (100000, 8), (100000, 3), (4096, 8), (17, 2), (10**7, 8)])
+def test_shard_bounds_partition(n, world):
+    edges = [w.shard_bounds(n, r, world) for r in range(world)]
+    assert edges[0][0] == 0 and edges[-1][1] == n
+    for (lo, hi), (lo2, _) in zip(edges, edges[1:]):
+        assert hi == lo2 and lo <= hi
+    sizes = [hi - lo for lo, hi in edges]
+    assert max(sizes) - min(sizes) <= 16 or n < 16 * world
+    for lo, hi in edges[:-1]:
+        assert lo % 16 == 0 or lo == n

@@ -1,0 +1,669 @@
+// wd_api.cu -- host dispatcher + C ABI of libwignerd_b200.so (see include/wignerd_b200.h).
+//
+// Layering: C ABI -> handle (device, stream, per-j plan cache, mutex) -> kernels in wd_kernels.cuh.
+// No CPU compute path exists in this file: every entry point that produces d/D values launches
+// sm_100a kernels, and fails with WD_ERR_CUDA when no device is usable.
+#include "../../../include/wignerd_b200.h"
+#include "wd_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace wd;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(e_ == cudaErrorMemoryAllocation ? WD_ERR_NOMEM : WD_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                  \
+    } while (0)
+
+constexpr int kMaxTwoJ = 4094;
+
+struct Plan {
+    PlanDev dev{};
+    double *uq = nullptr, *mu = nullptr, *w = nullptr;
+};
+
+}  // namespace
+
+struct wd_handle_s {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    std::mutex mtx;
+    std::map<int, Plan> plans;
+    int num_sms = 0;
+    size_t smem_optin = 0;
+    int64_t launches = 0;
+    int variant = 0;
+    PlanDev *d_table = nullptr;      // plan table indexed by twoj, for K4
+    int table_max = -1;
+    bool table_dirty = true;
+    int *d_flag = nullptr;           // error flag / scratch ints
+    bool attr_set[2][2] = {{false, false}, {false, false}};
+};
+
+namespace {
+
+void plan_dims(int twoj, PlanDev &p)
+{
+    p.twoj = twoj;
+    p.N = twoj + 1;
+    p.Q = (p.N + 1) / 2;
+    const int K = p.Q;
+    p.K0 = (K + 1) / 2;
+    p.K1 = K / 2;
+    p.K0p = wd_round4(p.K0);
+    p.K1p = wd_round4(p.K1);
+    p.Kp = p.K0p + p.K1p;
+    p.ldu = p.Kp + 2;
+    p.zskip = (twoj & 1) ? 0 : 1;
+}
+
+// Build the tables for all missing twoj of the list with ONE launch of the batched eigensolver.
+int prepare_locked(wd_handle_t h, const int32_t *list, int nj)
+{
+    std::vector<int> todo;
+    for (int i = 0; i < nj; ++i) {
+        const int tj = list[i];
+        if (tj < 0) return fail(WD_ERR_ASSERT, "j must be >= 0 (got 2j = %d)", tj);
+        if (tj > kMaxTwoJ) return fail(WD_ERR_UNSUPPORTED, "2j = %d exceeds the supported maximum %d", tj, kMaxTwoJ);
+        if (!h->plans.count(tj) && std::find(todo.begin(), todo.end(), tj) == todo.end()) todo.push_back(tj);
+    }
+    if (todo.empty()) return WD_OK;
+    CU(cudaSetDevice(h->device));
+    std::vector<EigJob> jobs(todo.size());
+    std::vector<Plan> fresh(todo.size());
+    size_t scratch_total = 0;
+    int maxK = 1;
+    for (size_t t = 0; t < todo.size(); ++t) {
+        Plan &pl = fresh[t];
+        plan_dims(todo[t], pl.dev);
+        scratch_total += 2 * (size_t)pl.dev.N * pl.dev.Q;
+        maxK = std::max(maxK, pl.dev.Q);
+    }
+    double *scratch = nullptr, *tables = nullptr;
+    // one allocation per plan keeps wd_cache_clear simple; scratch is one block
+    CU(cudaMalloc(&scratch, scratch_total * sizeof(double)));
+    size_t off = 0;
+    for (size_t t = 0; t < todo.size(); ++t) {
+        Plan &pl = fresh[t];
+        const PlanDev &d = pl.dev;
+        const size_t nuq = (size_t)d.Q * d.ldu;
+        cudaError_t e = cudaMalloc(&tables, (nuq + 2 * (size_t)d.Kp) * sizeof(double));
+        if (e != cudaSuccess) {
+            cudaFree(scratch);
+            for (size_t s = 0; s < t; ++s) cudaFree(fresh[s].uq);
+            return fail(WD_ERR_NOMEM, "cudaMalloc of the j tables failed: %s", cudaGetErrorString(e));
+        }
+        pl.uq = tables;
+        pl.mu = tables + nuq;
+        pl.w = pl.mu + d.Kp;
+        pl.dev.uq = pl.uq;
+        pl.dev.mu = pl.mu;
+        pl.dev.w = pl.w;
+        cudaMemsetAsync(pl.uq, 0, nuq * sizeof(double), h->stream);
+        EigJob &jb = jobs[t];
+        jb.twoj = d.twoj; jb.N = d.N; jb.K = d.Q; jb.K0p = d.K0p; jb.ldu = d.ldu; jb.Kp = d.Kp;
+        jb.uq = pl.uq; jb.mu = pl.mu; jb.w = pl.w;
+        jb.scratch = scratch + off;
+        off += 2 * (size_t)d.N * d.Q;
+    }
+    EigJob *d_jobs = nullptr;
+    CU(cudaMalloc(&d_jobs, jobs.size() * sizeof(EigJob)));
+    CU(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(EigJob), cudaMemcpyHostToDevice, h->stream));
+    // grid.y is limited to 65535: launch in slices
+    for (size_t j0 = 0; j0 < jobs.size(); j0 += 32768) {
+        const unsigned ny = (unsigned)std::min<size_t>(32768, jobs.size() - j0);
+        dim3 grid((maxK + 127) / 128, ny);
+        k1_eig_kernel<<<grid, 128, 0, h->stream>>>(d_jobs + j0);
+        h->launches++;
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(d_jobs);
+    cudaFree(scratch);
+    for (size_t t = 0; t < todo.size(); ++t) h->plans[todo[t]] = fresh[t];
+    h->table_dirty = true;
+    return WD_OK;
+}
+
+int get_plan(wd_handle_t h, int twoj, const Plan **out)
+{
+    int32_t tj = twoj;
+    int rc = prepare_locked(h, &tj, 1);
+    if (rc) return rc;
+    *out = &h->plans[twoj];
+    return WD_OK;
+}
+
+bool dmma_fits(wd_handle_t h, const PlanDev &p, bool cplx, size_t *bytes)
+{
+    const K2Smem L = k2_smem_layout(p.Q, p.Kp, p.ldu, cplx);
+    *bytes = (size_t)L.total * sizeof(double);
+    return *bytes <= h->smem_optin;
+}
+
+template <bool HALF, bool CPLX>
+int launch_dmma(wd_handle_t h, const K2Args &a, size_t smem)
+{
+    if (!h->attr_set[HALF][CPLX]) {
+        CU(cudaFuncSetAttribute(k2_dmma_kernel<HALF, CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)h->smem_optin));
+        h->attr_set[HALF][CPLX] = true;
+    }
+    const long long nchunks = (a.nb + K2_ANG - 1) / K2_ANG;
+    const int grid = (int)std::min<long long>(nchunks, h->num_sms);
+    k2_dmma_kernel<HALF, CPLX><<<grid, K2_THREADS, smem, h->stream>>>(a);
+    h->launches++;
+    CU(cudaGetLastError());
+    return WD_OK;
+}
+
+// d (or D) for nb generic angles, all pointers on the device.
+int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const double *beta, const double *gamma,
+                    long long nb, double *out, bool cplx, bool equator)
+{
+    if (nb <= 0) return WD_OK;
+    K2Args a;
+    a.p = pl.dev;
+    a.alpha = alpha; a.beta = beta; a.gamma = gamma;
+    a.nb = nb; a.out = out; a.equator = equator ? 1 : 0;
+    size_t smem = 0;
+    const bool fits = dmma_fits(h, pl.dev, cplx, &smem);
+    int variant = h->variant;
+    if (variant == 2 && !fits) return fail(WD_ERR_UNSUPPORTED, "2j = %d does not fit the DMMA kernel (%zu B of shared memory)", pl.dev.twoj, smem);
+    const bool use_dmma = (variant == 2) || (variant == 0 && fits);
+    const bool half = pl.dev.twoj & 1;
+    if (use_dmma) {
+        if (half) return cplx ? launch_dmma<true, true>(h, a, smem) : launch_dmma<true, false>(h, a, smem);
+        return cplx ? launch_dmma<false, true>(h, a, smem) : launch_dmma<false, false>(h, a, smem);
+    }
+    const size_t psm = 2 * (size_t)pl.dev.Kp * sizeof(double);
+    const int Q = pl.dev.Q;
+    const int gy = std::max(1, std::min(64, (Q * Q + 255) / 256));
+    for (long long b0 = 0; b0 < nb; b0 += 1 << 30) {     // grid.x limit
+        K2Args s = a;
+        const long long cnt = std::min<long long>(nb - b0, 1 << 30);
+        s.beta = beta + b0; s.nb = cnt;
+        if (cplx) { s.alpha = alpha + b0; s.gamma = gamma + b0; }
+        s.out = out + (size_t)b0 * pl.dev.N * pl.dev.N * (cplx ? 2 : 1);
+        dim3 grid((unsigned)cnt, gy);
+        if (cplx) k2_plain_kernel<true><<<grid, 256, psm, h->stream>>>(s);
+        else k2_plain_kernel<false><<<grid, 256, psm, h->stream>>>(s);
+        h->launches++;
+    }
+    CU(cudaGetLastError());
+    return WD_OK;
+}
+
+// host-memory front end: angles H2D, slabs of output computed on the device and copied back, double-buffered.
+int contract_host(wd_handle_t h, const Plan &pl, const double *alpha, const double *beta, const double *gamma,
+                  long long nb, double *out, bool cplx, bool equator)
+{
+    if (nb <= 0) return WD_OK;
+    CU(cudaSetDevice(h->device));
+    const size_t per = (size_t)pl.dev.N * pl.dev.N * (cplx ? 2 : 1);          // doubles per matrix
+    const int nang = cplx ? 3 : 1;
+    double *d_ang = nullptr;
+    CU(cudaMalloc(&d_ang, (size_t)nb * nang * sizeof(double)));
+    cudaMemcpyAsync(d_ang, beta, nb * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (cplx) {
+        cudaMemcpyAsync(d_ang + nb, alpha, nb * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyAsync(d_ang + 2 * nb, gamma, nb * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    }
+    const size_t slab_bytes_target = (size_t)512 << 20;
+    long long slab = std::max<long long>(1, (long long)(slab_bytes_target / (per * sizeof(double))));
+    slab = std::min(slab, nb);
+    if (slab > K2_ANG) slab -= slab % K2_ANG;
+    const int nbuf = (slab < nb) ? 2 : 1;
+    double *d_out[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    int rc = WD_OK;
+    for (int i = 0; i < nbuf && rc == WD_OK; ++i) {
+        if (cudaMalloc(&d_out[i], (size_t)slab * per * sizeof(double)) != cudaSuccess)
+            rc = fail(WD_ERR_NOMEM, "cudaMalloc of a %zu-byte output slab failed", (size_t)slab * per * sizeof(double));
+        cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
+    }
+    int k = 0;
+    for (long long b0 = 0; b0 < nb && rc == WD_OK; b0 += slab, ++k) {
+        const int i = k % nbuf;
+        const long long cnt = std::min(slab, nb - b0);
+        if (k >= nbuf) cudaStreamWaitEvent(h->stream, copied[i], 0);        // slab buffer free again
+        rc = contract_device(h, pl, cplx ? d_ang + nb + b0 : nullptr, d_ang + b0, cplx ? d_ang + 2 * nb + b0 : nullptr,
+                             cnt, d_out[i], cplx, equator);
+        if (rc) break;
+        cudaEventRecord(done[i], h->stream);
+        cudaStreamWaitEvent(h->copy_stream, done[i], 0);
+        cudaMemcpyAsync(out + (size_t)b0 * per, d_out[i], (size_t)cnt * per * sizeof(double), cudaMemcpyDeviceToHost,
+                        h->copy_stream);
+        cudaEventRecord(copied[i], h->copy_stream);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(h->stream), e2 = cudaStreamSynchronize(h->copy_stream);
+    for (int i = 0; i < nbuf; ++i) {
+        if (d_out[i]) cudaFree(d_out[i]);
+        if (done[i]) cudaEventDestroy(done[i]);
+        if (copied[i]) cudaEventDestroy(copied[i]);
+    }
+    cudaFree(d_ang);
+    if (rc) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess)
+        return fail(WD_ERR_CUDA, "contraction failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    return WD_OK;
+}
+
+__global__ void pole_kernel(double *D, int twoj, int kind, int cplx, double alpha, double gamma)
+{
+    // wignerd!(…, NorthPole/SouthPole) (src/WignerD.jl:247-264) then, for complex D, the phase loop :338-340
+    const int N = twoj + 1;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < N * N; e += gridDim.x * blockDim.x) {
+        const int row = e % N, col = e / N;
+        if (kind == WD_BETA_NORTH && row == col) {
+            if (cplx) { D[2 * e] = 1.0; D[2 * e + 1] = 0.0; } else D[e] = 1.0;
+        }
+        if (kind == WD_BETA_SOUTH && row + col == N - 1) {
+            const double v = (row & 1) ? -1.0 : 1.0;       // + at m = -j, alternating
+            if (cplx) { D[2 * e] = v; D[2 * e + 1] = 0.0; } else D[e] = v;
+        }
+        if (cplx) {
+            const double m = 0.5 * (double)(2 * row - twoj), n = 0.5 * (double)(2 * col - twoj);
+            double s, c;
+            sincos(-(m * alpha + n * gamma), &s, &c);
+            const double re = D[2 * e], im = D[2 * e + 1];
+            D[2 * e] = re * c - im * s;
+            D[2 * e + 1] = re * s + im * c;
+        }
+    }
+}
+
+__global__ void maxabs_i32_kernel(const int32_t *v, long long n, int *out)
+{
+    int m = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = max(m, v[i] < 0 ? 0x7fffffff : v[i]);
+    atomicMax(out, m);
+}
+
+int ensure_table(wd_handle_t h, int max_twoj)
+{
+    if (!h->table_dirty && h->table_max >= max_twoj) return WD_OK;
+    int top = -1;
+    for (auto &kv : h->plans) top = std::max(top, kv.first);
+    std::vector<PlanDev> tab((size_t)top + 1);
+    for (auto &t : tab) { memset(&t, 0, sizeof t); }
+    for (auto &kv : h->plans) tab[kv.first] = kv.second.dev;
+    if (h->d_table) cudaFree(h->d_table);
+    h->d_table = nullptr;
+    CU(cudaMalloc(&h->d_table, std::max<size_t>(1, tab.size()) * sizeof(PlanDev)));
+    CU(cudaMemcpy(h->d_table, tab.data(), tab.size() * sizeof(PlanDev), cudaMemcpyHostToDevice));
+    h->table_max = top;
+    h->table_dirty = false;
+    return WD_OK;
+}
+
+int jmn_common(wd_handle_t h, const int32_t *twoj, const int32_t *twom, const int32_t *twon, const double *alpha,
+               const double *beta, const double *gamma, int64_t n, int beta_kind, double *out, int mem, bool cplx)
+{
+    if (!h) return fail(WD_ERR_ASSERT, "null handle");
+    if (n < 0) return fail(WD_ERR_ASSERT, "negative tuple count");
+    if (n == 0) return WD_OK;
+    if (!twoj || !twom || !twon || !out || (beta_kind == WD_BETA_GENERIC && !beta) || (cplx && (!alpha || !gamma)))
+        return fail(WD_ERR_ASSERT, "null pointer argument");
+    if (beta_kind < 0 || beta_kind > 3) return fail(WD_ERR_ASSERT, "bad beta_kind %d", beta_kind);
+    std::lock_guard<std::mutex> lk(h->mtx);
+    CU(cudaSetDevice(h->device));
+    const int32_t *d_tj = twoj, *d_tm = twom, *d_tn = twon;
+    const double *d_a = alpha, *d_b = beta, *d_g = gamma;
+    double *d_out = out;
+    void *blk = nullptr;
+    const size_t osz = (cplx ? 2 : 1) * sizeof(double) * (size_t)n;
+    if (mem == WD_MEM_HOST) {
+        const size_t isz = sizeof(int32_t) * (size_t)n, dsz = sizeof(double) * (size_t)n;
+        const size_t total = 3 * isz + 3 * dsz + osz + 64;
+        CU(cudaMalloc(&blk, total));
+        char *pch = (char *)blk;
+        double *pb = (double *)pch; pch += dsz;
+        double *pa = (double *)pch; pch += dsz;
+        double *pg = (double *)pch; pch += dsz;
+        double *po = (double *)pch; pch += osz;
+        int32_t *pj = (int32_t *)pch; pch += isz;
+        int32_t *pm = (int32_t *)pch; pch += isz;
+        int32_t *pn = (int32_t *)pch;
+        cudaMemcpyAsync(pj, twoj, isz, cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyAsync(pm, twom, isz, cudaMemcpyHostToDevice, h->stream);
+        cudaMemcpyAsync(pn, twon, isz, cudaMemcpyHostToDevice, h->stream);
+        if (beta) cudaMemcpyAsync(pb, beta, dsz, cudaMemcpyHostToDevice, h->stream);
+        if (cplx) {
+            cudaMemcpyAsync(pa, alpha, dsz, cudaMemcpyHostToDevice, h->stream);
+            cudaMemcpyAsync(pg, gamma, dsz, cudaMemcpyHostToDevice, h->stream);
+        }
+        d_tj = pj; d_tm = pm; d_tn = pn; d_a = pa; d_b = pb; d_g = pg; d_out = po;
+    }
+    int rc = WD_OK;
+    int hflag[2] = {0, 0};
+    do {
+        // poles never touch the eigenvectors (src/WignerD.jl:218-228): no tables needed
+        int maxtj = -1;
+        if (beta_kind == WD_BETA_GENERIC || beta_kind == WD_BETA_EQUATOR) {
+            cudaMemsetAsync(h->d_flag, 0, 2 * sizeof(int), h->stream);
+            maxabs_i32_kernel<<<std::min<long long>(1024, (n + 255) / 256), 256, 0, h->stream>>>(d_tj, n, h->d_flag + 1);
+            h->launches++;
+            if (cudaMemcpyAsync(hflag, h->d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+                cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = fail(WD_ERR_CUDA, "max(2j) scan failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+            maxtj = hflag[1];
+            if (maxtj == 0x7fffffff) { rc = fail(WD_ERR_ASSERT, "j must be >= 0"); break; }
+            if (maxtj > kMaxTwoJ) { rc = fail(WD_ERR_UNSUPPORTED, "2j = %d exceeds the supported maximum %d", maxtj, kMaxTwoJ); break; }
+            std::vector<int32_t> all((size_t)maxtj + 1);
+            for (int i = 0; i <= maxtj; ++i) all[i] = i;
+            rc = prepare_locked(h, all.data(), (int)all.size());
+            if (rc) break;
+            rc = ensure_table(h, maxtj);
+            if (rc) break;
+        } else {
+            cudaMemsetAsync(h->d_flag, 0, 2 * sizeof(int), h->stream);
+        }
+        K4Args a;
+        a.plans = h->d_table; a.max_twoj = maxtj;
+        a.twoj = d_tj; a.twom = d_tm; a.twon = d_tn;
+        a.beta = d_b; a.alpha = d_a; a.gamma = d_g;
+        a.n = n; a.beta_kind = beta_kind; a.out = d_out; a.err = h->d_flag;
+        const int blocks = (int)std::min<long long>((n + 7) / 8, (long long)h->num_sms * 8);
+        if (cplx) k4_jmn_kernel<true><<<blocks, 256, 0, h->stream>>>(a);
+        else k4_jmn_kernel<false><<<blocks, 256, 0, h->stream>>>(a);
+        h->launches++;
+        if (mem == WD_MEM_HOST) cudaMemcpyAsync(out, d_out, osz, cudaMemcpyDeviceToHost, h->stream);
+        cudaMemcpyAsync(hflag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { rc = fail(WD_ERR_CUDA, "jmn kernel failed: %s", cudaGetErrorString(e)); break; }
+        if (hflag[0]) rc = fail(WD_ERR_ARGUMENT, "m or n is inconsistent with j for at least one tuple");
+    } while (0);
+    if (blk) cudaFree(blk);
+    return rc;
+}
+
+}  // namespace
+
+// ======================================================================================================
+// C ABI
+// ======================================================================================================
+extern "C" {
+
+const char *wd_last_error(void) { return g_err.c_str(); }
+int wd_abi_version(void) { return 1; }
+
+int wd_create(int device, wd_handle_t *out)
+{
+    if (!out) return fail(WD_ERR_ASSERT, "null output pointer");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(WD_ERR_CUDA, "no CUDA device is usable (%s); this library has no CPU path", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(WD_ERR_ASSERT, "device %d out of range (0..%d)", device, ndev - 1);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(WD_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    wd_handle_t h = new wd_handle_s;
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    CU(cudaMalloc(&h->d_flag, 4 * sizeof(int)));
+    *out = h;
+    return WD_OK;
+}
+
+int wd_destroy(wd_handle_t h)
+{
+    if (!h) return WD_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto &kv : h->plans) cudaFree(kv.second.uq);
+    if (h->d_table) cudaFree(h->d_table);
+    if (h->d_flag) cudaFree(h->d_flag);
+    cudaStreamDestroy(h->own_stream);
+    cudaStreamDestroy(h->copy_stream);
+    delete h;
+    return WD_OK;
+}
+
+int wd_set_stream(wd_handle_t h, void *s)
+{
+    if (!h) return fail(WD_ERR_ASSERT, "null handle");
+    std::lock_guard<std::mutex> lk(h->mtx);
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return WD_OK;
+}
+
+int wd_synchronize(wd_handle_t h)
+{
+    if (!h) return fail(WD_ERR_ASSERT, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(h->copy_stream));
+    return WD_OK;
+}
+
+int64_t wd_launch_count(wd_handle_t h) { return h ? h->launches : 0; }
+
+int wd_cache_clear(wd_handle_t h)
+{
+    if (!h) return fail(WD_ERR_ASSERT, "null handle");
+    std::lock_guard<std::mutex> lk(h->mtx);
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto &kv : h->plans) cudaFree(kv.second.uq);
+    h->plans.clear();
+    h->table_dirty = true;
+    return WD_OK;
+}
+
+int wd_set_variant(wd_handle_t h, int variant)
+{
+    if (!h) return fail(WD_ERR_ASSERT, "null handle");
+    if (variant < 0 || variant > 2) return fail(WD_ERR_ASSERT, "variant must be 0, 1 or 2");
+    h->variant = variant;
+    return WD_OK;
+}
+
+int wd_prepare(wd_handle_t h, const int32_t *twoj_list, int32_t nj)
+{
+    if (!h) return fail(WD_ERR_ASSERT, "null handle");
+    if (nj < 0 || (nj > 0 && !twoj_list)) return fail(WD_ERR_ASSERT, "bad j list");
+    std::lock_guard<std::mutex> lk(h->mtx);
+    return prepare_locked(h, twoj_list, nj);
+}
+
+int wd_eigvecs(wd_handle_t h, int32_t twoj, double *u_out)
+{
+    if (!h || !u_out) return fail(WD_ERR_ASSERT, "null argument");
+    std::lock_guard<std::mutex> lk(h->mtx);
+    const Plan *pl;
+    int rc = get_plan(h, twoj, &pl);
+    if (rc) return rc;
+    const PlanDev &d = pl->dev;
+    std::vector<double> uq((size_t)d.Q * d.ldu);
+    CU(cudaMemcpy(uq.data(), pl->uq, uq.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    const int N = d.N, K = d.Q, i0 = N - d.Q, k0 = N - K;
+    for (int kappa = 0; kappa < K; ++kappa) {
+        const int kp = wd_kp_of_kappa(kappa, K, d.K0p);
+        const double eps = (kp < d.K0p) ? 1.0 : -1.0;        // u[-m] = eps u[m]
+        const int k = k0 + kappa, kmir = N - 1 - k;          // mu and -mu columns
+        for (int i = 0; i < N; ++i) {
+            const double v = (i >= i0) ? uq[(size_t)(i - i0) * d.ldu + kp] : eps * uq[(size_t)(N - 1 - i - i0) * d.ldu + kp];
+            u_out[i + (size_t)N * k] = v;
+            if (kmir != k) u_out[i + (size_t)N * kmir] = (i & 1) ? -v : v;    // u[i,-mu] = (-1)^i u[i,mu]
+        }
+    }
+    return WD_OK;
+}
+
+static int matrices(wd_handle_t h, int32_t twoj, const double *alpha, const double *beta, const double *gamma,
+                    int64_t nb, double *out, int mem, bool cplx, bool equator)
+{
+    if (!h) return fail(WD_ERR_ASSERT, "null handle");
+    if (nb < 0) return fail(WD_ERR_ASSERT, "negative batch size");
+    if (nb == 0) return WD_OK;
+    if (!beta || !out || (cplx && (!alpha || !gamma))) return fail(WD_ERR_ASSERT, "null pointer argument");
+    if (mem != WD_MEM_HOST && mem != WD_MEM_DEVICE) return fail(WD_ERR_ASSERT, "bad mem flag %d", mem);
+    std::lock_guard<std::mutex> lk(h->mtx);
+    const Plan *pl;
+    int rc = get_plan(h, twoj, &pl);
+    if (rc) return rc;
+    CU(cudaSetDevice(h->device));
+    if (mem == WD_MEM_DEVICE) return contract_device(h, *pl, alpha, beta, gamma, nb, out, cplx, equator);
+    return contract_host(h, *pl, alpha, beta, gamma, nb, out, cplx, equator);
+}
+
+int wd_d_batch(wd_handle_t h, int32_t twoj, const double *beta, int64_t nb, double *out, int mem)
+{
+    return matrices(h, twoj, nullptr, beta, nullptr, nb, out, mem, false, false);
+}
+
+int wd_D_batch(wd_handle_t h, int32_t twoj, const double *alpha, const double *beta, const double *gamma, int64_t nb,
+               double *out, int mem)
+{
+    return matrices(h, twoj, alpha, beta, gamma, nb, out, mem, true, false);
+}
+
+static int pole_matrix(wd_handle_t h, int32_t twoj, int kind, bool cplx, double alpha, double gamma, double *D)
+{
+    // the eigen step still runs first in the reference (:306-307); keep the cache behaviour identical
+    std::lock_guard<std::mutex> lk(h->mtx);
+    const Plan *pl;
+    int rc = get_plan(h, twoj, &pl);
+    if (rc) return rc;
+    CU(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)pl->dev.N * pl->dev.N * (cplx ? 2 : 1) * sizeof(double);
+    double *d_D = nullptr;
+    CU(cudaMalloc(&d_D, bytes));
+    cudaMemcpyAsync(d_D, D, bytes, cudaMemcpyHostToDevice, h->stream);
+    pole_kernel<<<std::max(1, std::min(64, (pl->dev.N * pl->dev.N + 255) / 256)), 256, 0, h->stream>>>(d_D, twoj, kind, cplx ? 1 : 0, alpha, gamma);
+    h->launches++;
+    cudaMemcpyAsync(D, d_D, bytes, cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_D);
+    if (e != cudaSuccess) return fail(WD_ERR_CUDA, "pole fill failed: %s", cudaGetErrorString(e));
+    return WD_OK;
+}
+
+int wd_d_matrix(wd_handle_t h, int32_t twoj, double beta, int beta_kind, double *d)
+{
+    if (!h || !d) return fail(WD_ERR_ASSERT, "null argument");
+    if (twoj < 0) return fail(WD_ERR_ASSERT, "j must be >= 0");
+    switch (beta_kind) {
+    case WD_BETA_GENERIC: return matrices(h, twoj, nullptr, &beta, nullptr, 1, d, WD_MEM_HOST, false, false);
+    case WD_BETA_EQUATOR: { const double b = 1.5707963267948966; return matrices(h, twoj, nullptr, &b, nullptr, 1, d, WD_MEM_HOST, false, true); }
+    case WD_BETA_NORTH:
+    case WD_BETA_SOUTH: return pole_matrix(h, twoj, beta_kind, false, 0.0, 0.0, d);
+    default: return fail(WD_ERR_ASSERT, "bad beta_kind %d", beta_kind);
+    }
+}
+
+int wd_D_matrix(wd_handle_t h, int32_t twoj, double alpha, double beta, int beta_kind, double gamma, double *D)
+{
+    if (!h || !D) return fail(WD_ERR_ASSERT, "null argument");
+    if (twoj < 0) return fail(WD_ERR_ASSERT, "j must be >= 0");
+    switch (beta_kind) {
+    case WD_BETA_GENERIC: return matrices(h, twoj, &alpha, &beta, &gamma, 1, D, WD_MEM_HOST, true, false);
+    case WD_BETA_EQUATOR: { const double b = 1.5707963267948966; return matrices(h, twoj, &alpha, &b, &gamma, 1, D, WD_MEM_HOST, true, true); }
+    case WD_BETA_NORTH:
+    case WD_BETA_SOUTH: return pole_matrix(h, twoj, beta_kind, true, alpha, gamma, D);
+    default: return fail(WD_ERR_ASSERT, "bad beta_kind %d", beta_kind);
+    }
+}
+
+int wd_d_multi(wd_handle_t h, const int32_t *twoj_list, int32_t nj, const double *beta, int64_t nb, double *out,
+               const int64_t *offsets, int mem)
+{
+    if (!h) return fail(WD_ERR_ASSERT, "null handle");
+    if (nj < 0 || nb < 0) return fail(WD_ERR_ASSERT, "negative count");
+    if (nj == 0 || nb == 0) return WD_OK;
+    if (!twoj_list || !beta || !out || !offsets) return fail(WD_ERR_ASSERT, "null pointer argument");
+    std::lock_guard<std::mutex> lk(h->mtx);
+    int rc = prepare_locked(h, twoj_list, nj);
+    if (rc) return rc;
+    CU(cudaSetDevice(h->device));
+    if (mem == WD_MEM_DEVICE) {
+        for (int k = 0; k < nj; ++k) {
+            rc = contract_device(h, h->plans[twoj_list[k]], nullptr, beta, nullptr, nb, out + offsets[k], false, false);
+            if (rc) return rc;
+        }
+        return WD_OK;
+    }
+    for (int k = 0; k < nj; ++k) {
+        rc = contract_host(h, h->plans[twoj_list[k]], nullptr, beta, nullptr, nb, out + offsets[k], false, false);
+        if (rc) return rc;
+    }
+    return WD_OK;
+}
+
+int wd_djmn_batch(wd_handle_t h, const int32_t *twoj, const int32_t *twom, const int32_t *twon, const double *beta,
+                  int64_t n, int beta_kind, double *out, int mem)
+{
+    return jmn_common(h, twoj, twom, twon, nullptr, beta, nullptr, n, beta_kind, out, mem, false);
+}
+
+int wd_Djmn_batch(wd_handle_t h, const int32_t *twoj, const int32_t *twom, const int32_t *twon, const double *alpha,
+                  const double *beta, const double *gamma, int64_t n, int beta_kind, double *out, int mem)
+{
+    return jmn_common(h, twoj, twom, twon, alpha, beta, gamma, n, beta_kind, out, mem, true);
+}
+
+int wd_fp64_peak(wd_handle_t h, int kind, int iters, double *tflops)
+{
+    if (!h || !tflops) return fail(WD_ERR_ASSERT, "null argument");
+    std::lock_guard<std::mutex> lk(h->mtx);
+    CU(cudaSetDevice(h->device));
+    double *sink = nullptr;
+    CU(cudaMalloc(&sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int blocks = h->num_sms * 4, threads = 256;
+    fp64_peak_kernel<<<blocks, threads, 0, h->stream>>>(kind, 16, sink);   // warm-up
+    cudaEventRecord(e0, h->stream);
+    fp64_peak_kernel<<<blocks, threads, 0, h->stream>>>(kind, iters, sink);
+    cudaEventRecord(e1, h->stream);
+    h->launches += 2;
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    if (e != cudaSuccess) return fail(WD_ERR_CUDA, "peak kernel failed: %s", cudaGetErrorString(e));
+    const double warps = (double)blocks * threads / 32.0;
+    const double flops = (kind == 0) ? warps * iters * 8.0 * 512.0 : (double)blocks * threads * iters * 16.0 * 2.0;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    return WD_OK;
+}
+
+}  // extern "C"
