@@ -65,7 +65,7 @@ int wd_create(int device, wd_handle_t *out);
 int wd_destroy(wd_handle_t h);
 const char *wd_last_error(void);
 int wd_abi_version(void);
-/* enqueue on a caller-owned cudaStream_t (0/NULL = the handle's own stream) */
+/* enqueue on a caller-owned cudaStream_t (0/NULL = the handle's own stream; pass cudaStreamLegacy (0x1) for the default stream) */
 int wd_set_stream(wd_handle_t h, void *cuda_stream);
 int wd_synchronize(wd_handle_t h);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */

@@ -258,6 +258,12 @@ class Engine:
     def set_stream(self, cuda_stream: int | None):
         _check(self._lib.wd_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
 
+    def _use_torch_stream(self, device):
+        """enqueue on torch's current stream; the legacy default stream is passed as cudaStreamLegacy (0x1)
+        because 0 means "the handle's own stream" in wd_set_stream."""
+        import torch
+        self.set_stream(torch.cuda.current_stream(device).cuda_stream or 1)
+
     def synchronize(self):
         _check(self._lib.wd_synchronize(self._h))
 
@@ -321,7 +327,7 @@ class Engine:
             import torch
             if out is None:
                 out = torch.empty((nb, N, N), dtype=torch.float64, device=b.device)
-            self.set_stream(torch.cuda.current_stream(b.device).cuda_stream)
+            self._use_torch_stream(b.device)
         elif out is None:
             out = np.empty((nb, N, N), dtype=np.float64)
         _check(self._lib.wd_d_batch(self._h, twoj, _ptr(b), nb, _ptr(out), mem))
@@ -345,7 +351,7 @@ class Engine:
             import torch
             if out is None:
                 out = torch.empty((nb, N, N), dtype=torch.complex128, device=b.device)
-            self.set_stream(torch.cuda.current_stream(b.device).cuda_stream)
+            self._use_torch_stream(b.device)
         elif out is None:
             out = np.empty((nb, N, N), dtype=np.complex128)
         _check(self._lib.wd_D_batch(self._h, twoj, _ptr(a), _ptr(b), _ptr(g), nb, _ptr(out), mem))
@@ -366,7 +372,7 @@ class Engine:
             import torch
             if out is None:
                 out = torch.empty(total, dtype=torch.float64, device=b.device)
-            self.set_stream(torch.cuda.current_stream(b.device).cuda_stream)
+            self._use_torch_stream(b.device)
         elif out is None:
             out = np.empty(total, dtype=np.float64)
         _check(self._lib.wd_d_multi(self._h, _ptr(twojs), len(twojs), _ptr(b), nb, _ptr(out), _ptr(offsets), mem))
@@ -400,7 +406,7 @@ class Engine:
             import torch
             if out is None:
                 out = torch.empty(n, dtype=torch.float64, device=tj.device)
-            self.set_stream(torch.cuda.current_stream(tj.device).cuda_stream)
+            self._use_torch_stream(tj.device)
         elif out is None:
             out = np.empty(n, dtype=np.float64)
         _check(self._lib.wd_djmn_batch(self._h, _ptr(tj), _ptr(tm), _ptr(tn), _ptr(b), n, int(beta_kind), _ptr(out), mem))
@@ -418,7 +424,7 @@ class Engine:
             import torch
             if out is None:
                 out = torch.empty(n, dtype=torch.complex128, device=tj.device)
-            self.set_stream(torch.cuda.current_stream(tj.device).cuda_stream)
+            self._use_torch_stream(tj.device)
         elif out is None:
             out = np.empty(n, dtype=np.complex128)
         _check(self._lib.wd_Djmn_batch(self._h, _ptr(tj), _ptr(tm), _ptr(tn), _ptr(a), _ptr(b), _ptr(g), n,
@@ -478,9 +484,9 @@ class Engine:
         if kind in (GENERIC, EQUATOR):
             self._check_Jy(twoj, Jy)
         out = np.empty(1)
-        _check(self._lib.wd_djmn_batch(self._h, _ptr(np.array([twoj], np.int32)), _ptr(np.array([twom], np.int32)),
-                                       _ptr(np.array([twon], np.int32)), _ptr(np.array([float(beta)])), 1, kind,
-                                       _ptr(out), MEM_HOST))
+        tj, tm, tn = (np.array([v], np.int32) for v in (twoj, twom, twon))     # keep alive across the call
+        b = np.array([float(beta)])
+        _check(self._lib.wd_djmn_batch(self._h, _ptr(tj), _ptr(tm), _ptr(tn), _ptr(b), 1, kind, _ptr(out), MEM_HOST))
         return float(out[0])
 
     def wignerDjmn(self, j, m, n, alpha, beta, gamma, Jy=None) -> complex:
@@ -491,9 +497,9 @@ class Engine:
         if kind in (GENERIC, EQUATOR):
             self._check_Jy(twoj, Jy)
         out = np.empty(1, dtype=np.complex128)
-        _check(self._lib.wd_Djmn_batch(self._h, _ptr(np.array([twoj], np.int32)), _ptr(np.array([twom], np.int32)),
-                                       _ptr(np.array([twon], np.int32)), _ptr(np.array([float(alpha)])),
-                                       _ptr(np.array([float(beta)])), _ptr(np.array([float(gamma)])), 1, kind,
+        tj, tm, tn = (np.array([v], np.int32) for v in (twoj, twom, twon))     # keep alive across the call
+        a, b, g = (np.array([float(v)]) for v in (alpha, beta, gamma))
+        _check(self._lib.wd_Djmn_batch(self._h, _ptr(tj), _ptr(tm), _ptr(tn), _ptr(a), _ptr(b), _ptr(g), 1, kind,
                                        _ptr(out), MEM_HOST))
         return complex(out[0])
 

@@ -5,6 +5,7 @@
 // sm_100a kernels, and fails with WD_ERR_CUDA when no device is usable.
 #include "../../../include/wignerd_b200.h"
 #include "wd_kernels.cuh"
+#include "wd_k2_dmma.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -342,15 +343,16 @@ int jmn_common(wd_handle_t h, const int32_t *twoj, const int32_t *twom, const in
     const size_t osz = (cplx ? 2 : 1) * sizeof(double) * (size_t)n;
     if (mem == WD_MEM_HOST) {
         const size_t isz = sizeof(int32_t) * (size_t)n, dsz = sizeof(double) * (size_t)n;
-        const size_t total = 3 * isz + 3 * dsz + osz + 64;
+        auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };      // every sub-buffer 256-byte aligned
+        const size_t total = 3 * al(isz) + 3 * al(dsz) + al(osz);
         CU(cudaMalloc(&blk, total));
         char *pch = (char *)blk;
-        double *pb = (double *)pch; pch += dsz;
-        double *pa = (double *)pch; pch += dsz;
-        double *pg = (double *)pch; pch += dsz;
-        double *po = (double *)pch; pch += osz;
-        int32_t *pj = (int32_t *)pch; pch += isz;
-        int32_t *pm = (int32_t *)pch; pch += isz;
+        double *pb = (double *)pch; pch += al(dsz);
+        double *pa = (double *)pch; pch += al(dsz);
+        double *pg = (double *)pch; pch += al(dsz);
+        double *po = (double *)pch; pch += al(osz);
+        int32_t *pj = (int32_t *)pch; pch += al(isz);
+        int32_t *pm = (int32_t *)pch; pch += al(isz);
         int32_t *pn = (int32_t *)pch;
         cudaMemcpyAsync(pj, twoj, isz, cudaMemcpyHostToDevice, h->stream);
         cudaMemcpyAsync(pm, twom, isz, cudaMemcpyHostToDevice, h->stream);

@@ -17,7 +17,7 @@
 //                        which is what LAPACK zheevr -- the reference's eigen!, :161 -- ends in) at the
 //                        analytically known eigenvalues; one thread per eigenvector, all j in one launch.
 //   k2_plain_kernel      FP64-ALU contraction, any j (fallback + on-GPU cross-check).
-//   k2_dmma_kernel       the hot kernel: DMMA.8x8x4 contraction over (angle tile) x (m tile), UQ resident
+//   k2_dmma_kernel       (wd_k2_dmma.cuh) the hot kernel: DMMA.8x8x4 contraction over (angle tile) x (m tile), UQ resident
 //                        in shared memory, in-kernel trig tables, shared-memory staged coalesced stores,
 //                        optional fused exp(-i(m alpha + n gamma)) epilogue (complex D).
 //   k4_jmn_kernel        single elements (wignerdjmn / wignerDjmn): one warp per tuple.
@@ -206,279 +206,6 @@ __global__ void __launch_bounds__(256) k2_plain_kernel(K2Args a)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2 (DMMA): the hot kernel.
-//   CTA = 8 warps, persistent over chunks of 16 angles.  Shared memory: UQ (all of it), the mu / w
-//   vectors, the chunk's trig tables Tc/Ts[16][ldt] (w cos(mu beta), w sin(mu beta)), optional phase
-//   tables, and one staging tile per warp.
-//   Warp unit = one quadrant column qn  x  up to GMAX groups of 16 quadrant rows  x  16 angles.
-//   MMA roles (mma.sync m8n8k4 f64 -> SASS DMMA.8x8x4):  A[8 angles][4 kp] = T(beta, kp) * UQ[qn][kp],
-//   B[4 kp][8 rows] = UQ[row][kp], C[8 angles][8 rows].  A 16-row group is two tiles: the even rows and
-//   the odd rows (so one tile needs one trig function); a lane then owns 4 consecutive rows.
-// ------------------------------------------------------------------------------------------------
-constexpr int K2_WARPS = 8;
-constexpr int K2_THREADS = K2_WARPS * 32;
-constexpr int K2_ANG = 16;                 // angles per chunk (2 MMA row tiles)
-constexpr int K2_STG_LD = 66;              // staging row stride (doubles): == 2 mod 4, 16B-aligned rows
-constexpr int K2_STG_ROWS = 8;
-
-__device__ __forceinline__ void dmma(double (&d)[2], double a, double b)
-{
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-        : "+d"(d[0]), "+d"(d[1])
-        : "d"(a), "d"(b));
-}
-
-struct K2Smem {                 // offsets in doubles, computed identically on host and device
-    int uq, mu, w, tc, ts, ph, stg, total;
-    int ldt, qpad;
-};
-__host__ __device__ inline K2Smem k2_smem_layout(int Q, int Kp, int ldu, bool cplx)
-{
-    K2Smem s;
-    s.ldt = Kp | 4;                        // == 4 mod 8: conflict-free for 8 consecutive rows x 4 cols
-    s.qpad = (Q + 15) & ~15;               // UQ rows padded with zeros to whole 16-row groups
-    int o = 0;
-    s.uq = o;  o += s.qpad * ldu;
-    s.mu = o;  o += Kp;
-    s.w = o;   o += Kp;
-    s.tc = o;  o += K2_ANG * s.ldt;
-    s.ts = o;  o += K2_ANG * s.ldt;
-    s.ph = o;  o += cplx ? 4 * K2_ANG * Q : 0;          // cos(m a), sin(m a), cos(n g), sin(n g)  [16][Q]
-    o = (o + 1) & ~1;
-    s.stg = o; o += K2_WARPS * K2_STG_ROWS * K2_STG_LD;
-    s.total = o;
-    return s;
-}
-
-struct K2Ctx {                  // per-thread constants of the DMMA kernel
-    const double *sUQ, *sTc, *sTs, *sPh;
-    double *stg;
-    int ldu, ldt, N, Q, i0, zskip, Kp, K0p, twoj;
-    int lane, r, c;
-    long long b0;
-};
-
-// One warp unit: quadrant column qn, GC groups of 16 quadrant rows starting at group g0, 16 angles.
-template <bool HALF, bool CPLX, int GC>
-__device__ __forceinline__ void k2_unit(const K2Args &a, const K2Ctx &cx, const int qn, const int g0)
-{
-    constexpr int NALT = HALF ? 2 : 1;
-    const int ldu = cx.ldu, ldt = cx.ldt, r = cx.r, c = cx.c;
-    const int pe = qn & 1;
-    // even-row tiles pair with cos when qn is even, with sin when qn is odd
-    const double *tA = (pe ? cx.sTs : cx.sTc) + r * ldt + c;     // trig for the even-row tiles
-    const double *tB = (pe ? cx.sTc : cx.sTs) + r * ldt + c;     // trig for the odd-row tiles
-    const double *un = cx.sUQ + qn * ldu + c;
-    const double *ub = cx.sUQ + (16 * g0 + 2 * r) * ldu + c;     // even rows; odd rows at +ldu; groups at +16*ldu
-    const int gs = 16 * ldu, t8 = 8 * ldt;
-
-    double acc[2][2][GC][2][NALT][2];            // [class][angle tile][group][even/odd rows][main/alt][frag]
-#pragma unroll
-    for (int i = 0; i < 2 * 2 * GC * 2 * NALT * 2; ++i) (&acc[0][0][0][0][0][0])[i] = 0.0;
-
-#pragma unroll
-    for (int cls = 0; cls < 2; ++cls) {
-        const int kbeg = cls ? cx.K0p : 0;
-        const int kend = cls ? cx.Kp : cx.K0p;
-        // software pipeline: fragments of step k+4 are loaded while the DMMAs of step k issue.  The
-        // prefetch of the step after the last one reads (and discards) in-bounds shared memory.
-        double n_un = un[kbeg], n_ta[2], n_tb[2], n_be[GC], n_bo[GC];
-#pragma unroll
-        for (int ai = 0; ai < 2; ++ai) { n_ta[ai] = tA[ai * t8 + kbeg]; n_tb[ai] = tB[ai * t8 + kbeg]; }
-#pragma unroll
-        for (int g = 0; g < GC; ++g) { n_be[g] = ub[g * gs + kbeg]; n_bo[g] = ub[g * gs + ldu + kbeg]; }
-#pragma unroll 1
-        for (int k = kbeg; k < kend; k += 4) {
-            double fa[2], fb[2], be[GC], bo[GC];
-#pragma unroll
-            for (int ai = 0; ai < 2; ++ai) { fa[ai] = n_ta[ai] * n_un; fb[ai] = n_tb[ai] * n_un; }
-#pragma unroll
-            for (int g = 0; g < GC; ++g) { be[g] = n_be[g]; bo[g] = n_bo[g]; }
-            const int kn = k + 4;
-            n_un = un[kn];
-#pragma unroll
-            for (int ai = 0; ai < 2; ++ai) { n_ta[ai] = tA[ai * t8 + kn]; n_tb[ai] = tB[ai * t8 + kn]; }
-#pragma unroll
-            for (int g = 0; g < GC; ++g) { n_be[g] = ub[g * gs + kn]; n_bo[g] = ub[g * gs + ldu + kn]; }
-#pragma unroll
-            for (int g = 0; g < GC; ++g) {
-#pragma unroll
-                for (int ai = 0; ai < 2; ++ai) {
-                    dmma(acc[cls][ai][g][0][0], fa[ai], be[g]);
-                    dmma(acc[cls][ai][g][1][0], fb[ai], bo[g]);
-                    if (HALF) {
-                        dmma(acc[cls][ai][g][0][1], fb[ai], be[g]);
-                        dmma(acc[cls][ai][g][1][1], fa[ai], bo[g]);
-                    }
-                }
-            }
-        }
-    }
-
-    // ---- epilogue: butterfly, signs, stage through shared memory, coalesced stores ------------------
-    const int N = cx.N, Q = cx.Q, i0 = cx.i0, zskip = cx.zskip, lane = cx.lane;
-    double *stg = cx.stg;
-    const int ip = i0 + qn, ipr = N - 1 - ip;
-    const int qbase = 16 * g0;                     // first quadrant row of the unit
-    constexpr int span = 16 * GC;                  // rows covered (<= 64)
-#pragma unroll
-    for (int tgt = 0; tgt < 4; ++tgt) {
-        // tgt 0: ( i, i')  sum   ascending      tgt 1: (ir, i'r) sum  descending
-        // tgt 2: (ir, i')  dif   descending     tgt 3: ( i, i'r) dif  ascending
-        const bool desc = (tgt == 1 || tgt == 2);
-        const bool dif = (tgt >= 2);
-        const int col = (tgt == 0 || tgt == 2) ? ip : ipr;
-        if ((tgt == 1 || tgt == 3) && qn < zskip) continue;         // n = 0 mirrors onto itself (warp-uniform)
-        // global row of staging position s: ascending i0+qbase+s ; descending (N-1-i0-qbase-(span-1)) + s
-        const int row0 = desc ? (N - 1 - i0 - qbase - (span - 1)) : (i0 + qbase);
-        // sign: di of the lane's element t is +-(i0+qbase+16g+4c+t) ... only di mod 4 matters
-        const int dib = desc ? (N - 1 - i0 - qbase - col) : (i0 + qbase - col);
-#pragma unroll
-        for (int ai = 0; ai < 2; ++ai) {
-            __syncwarp();
-#pragma unroll
-            for (int g = 0; g < GC; ++g) {
-                double v[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int eo = t & 1, h = t >> 1;
-                    constexpr int dummy = 0; (void)dummy;
-                    const int alt = (HALF && dif) ? 1 : 0;
-                    const double p0 = acc[0][ai][g][eo][alt][h], p1 = acc[1][ai][g][eo][alt][h];
-                    const double x = dif ? (p0 - p1) : (p0 + p1);
-                    v[t] = flip(x, sigma_bit(desc ? (dib - t) : (dib + t)));
-                }
-                if (!desc) {
-                    double2 *dst = reinterpret_cast<double2 *>(stg + r * K2_STG_LD + 16 * g + 4 * c);
-                    dst[0] = make_double2(v[0], v[1]);
-                    dst[1] = make_double2(v[2], v[3]);
-                } else {
-                    double2 *dst = reinterpret_cast<double2 *>(stg + r * K2_STG_LD + (span - 4) - 16 * g - 4 * c);
-                    dst[0] = make_double2(v[3], v[2]);
-                    dst[1] = make_double2(v[1], v[0]);
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int ar = 0; ar < 8; ++ar) {
-                const long long b = cx.b0 + ai * 8 + ar;
-                if (b >= a.nb) break;              // warp-uniform
-#pragma unroll
-                for (int hh = 0; hh < (span + 31) / 32; ++hh) {
-                    const int s = hh * 32 + lane;
-                    if (s >= span) continue;
-                    const int qm = desc ? (qbase + span - 1 - s) : (qbase + s);
-                    if (qm >= Q || (desc && qm < zskip)) continue;
-                    const int row = row0 + s;
-                    double v = stg[ar * K2_STG_LD + s];
-                    if (a.equator && zskip) {
-                        const int j = cx.twoj >> 1;
-                        if ((col == j && (row & 1)) || (row == j && (col & 1))) v = 0.0;
-                    }
-                    const size_t e = ((size_t)b * N + col) * N + row;
-                    if (!CPLX) {
-                        a.out[e] = v;
-                    } else {
-                        // exp(-i(m alpha + n gamma)) = (ca - i sa)(cg - i sg); m -> -m flips sa, n -> -n flips sg
-                        const int ang = ai * 8 + ar;
-                        const bool mneg = row < i0;
-                        const int qr = mneg ? (N - 1 - row - i0) : (row - i0);
-                        const int qc = (col >= i0) ? (col - i0) : (N - 1 - col - i0);
-                        const double ca = cx.sPh[(0 * K2_ANG + ang) * Q + qr];
-                        double sa = cx.sPh[(1 * K2_ANG + ang) * Q + qr];
-                        const double cg = cx.sPh[(2 * K2_ANG + ang) * Q + qc];
-                        double sg = cx.sPh[(3 * K2_ANG + ang) * Q + qc];
-                        if (mneg) sa = -sa;
-                        if (col < i0) sg = -sg;
-                        const double cr = ca * cg - sa * sg;
-                        const double ci = -(sa * cg + ca * sg);
-                        reinterpret_cast<double2 *>(a.out)[e] = make_double2(v * cr, v * ci);
-                    }
-                }
-            }
-        }
-    }
-}
-
-template <bool HALF, bool CPLX>
-__global__ void __launch_bounds__(K2_THREADS, 1) k2_dmma_kernel(K2Args a)
-{
-    constexpr int GMAX = HALF ? 2 : 4;
-    extern __shared__ __align__(16) double sm[];
-    const PlanDev &p = a.p;
-    const int Q = p.Q, Kp = p.Kp, ldu = p.ldu;
-    const K2Smem L = k2_smem_layout(Q, Kp, ldu, CPLX);
-    const int ldt = L.ldt;
-    double *sUQ = sm + L.uq, *sMu = sm + L.mu, *sW = sm + L.w, *sTc = sm + L.tc, *sTs = sm + L.ts;
-    double *sPh = sm + L.ph;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    K2Ctx cx;
-    cx.sUQ = sUQ; cx.sTc = sTc; cx.sTs = sTs; cx.sPh = sPh;
-    cx.stg = sm + L.stg + warp * (K2_STG_ROWS * K2_STG_LD);
-    cx.ldu = ldu; cx.ldt = ldt; cx.N = p.N; cx.Q = Q; cx.i0 = p.N - Q; cx.zskip = p.zskip;
-    cx.Kp = Kp; cx.K0p = p.K0p; cx.twoj = p.twoj;
-    cx.lane = tid & 31; cx.r = cx.lane >> 2; cx.c = cx.lane & 3;
-
-    // one-time: UQ (+ zero pad rows), mu, w -> shared (16-byte vector copies; ldu and Kp are even)
-    {
-        const double2 *src = reinterpret_cast<const double2 *>(p.uq);
-        double2 *dst = reinterpret_cast<double2 *>(sUQ);
-        const int nvalid = (Q * ldu) / 2, nall = (L.qpad * ldu) / 2;
-        for (int i = tid; i < nall; i += K2_THREADS) dst[i] = (i < nvalid) ? src[i] : make_double2(0.0, 0.0);
-        for (int i = tid; i < Kp; i += K2_THREADS) { sMu[i] = p.mu[i]; sW[i] = p.w[i]; }
-    }
-    const int ngroups = L.qpad >> 4;
-    const int upc = (ngroups + GMAX - 1) / GMAX;          // units per column
-    const int nunits = Q * upc;
-    const long long nchunks = (a.nb + K2_ANG - 1) / K2_ANG;
-
-    for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-        const long long b0 = ch * K2_ANG;
-        cx.b0 = b0;
-        __syncthreads();                                   // previous chunk's readers are done (and UQ is in)
-        for (int idx = tid; idx < K2_ANG * Kp; idx += K2_THREADS) {
-            const int ang = idx / Kp, kp = idx - ang * Kp;
-            long long b = b0 + ang; if (b >= a.nb) b = a.nb - 1;
-            double s, cs;
-            sincos(sMu[kp] * a.beta[b], &s, &cs);         // fl(mu*beta) then sincos, like :199
-            const double w = sW[kp];
-            sTc[ang * ldt + kp] = w * cs;
-            sTs[ang * ldt + kp] = w * s;
-        }
-        if (CPLX) {
-            for (int idx = tid; idx < K2_ANG * Q; idx += K2_THREADS) {
-                const int ang = idx / Q, q = idx - ang * Q;
-                long long b = b0 + ang; if (b >= a.nb) b = a.nb - 1;
-                const double m = 0.5 * (double)(2 * q + (p.twoj & 1));
-                double s, cs;
-                sincos(m * a.alpha[b], &s, &cs);
-                sPh[(0 * K2_ANG + ang) * Q + q] = cs; sPh[(1 * K2_ANG + ang) * Q + q] = s;
-                sincos(m * a.gamma[b], &s, &cs);
-                sPh[(2 * K2_ANG + ang) * Q + q] = cs; sPh[(3 * K2_ANG + ang) * Q + q] = s;
-            }
-        }
-        __syncthreads();
-
-        for (int u = warp; u < nunits; u += K2_WARPS) {
-            const int qn = u / upc;
-            const int g0 = (u - qn * upc) * GMAX;
-            const int gcnt = min(GMAX, ngroups - g0);
-            if (HALF) {
-                if (gcnt == 2) k2_unit<HALF, CPLX, 2>(a, cx, qn, g0);
-                else k2_unit<HALF, CPLX, 1>(a, cx, qn, g0);
-            } else {
-                switch (gcnt) {
-                case 4: k2_unit<HALF, CPLX, 4>(a, cx, qn, g0); break;
-                case 3: k2_unit<HALF, CPLX, 3>(a, cx, qn, g0); break;
-                case 2: k2_unit<HALF, CPLX, HALF ? 1 : 2>(a, cx, qn, g0); break;
-                default: k2_unit<HALF, CPLX, 1>(a, cx, qn, g0); break;
-                }
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // K4: single elements.  One warp per tuple; lanes stride the padded mu axis.
 // ------------------------------------------------------------------------------------------------
 struct K4Args {
@@ -545,32 +272,6 @@ __global__ void __launch_bounds__(256) k4_jmn_kernel(K4Args a)
             }
         }
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// small helpers: pole fills (src/WignerD.jl:247-264) on device buffers, FP64 peak micro-benchmarks
-// ------------------------------------------------------------------------------------------------
-__global__ void fp64_peak_kernel(int kind, int iters, double *sink)
-{
-    double acc[8][2];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { acc[i][0] = threadIdx.x * 1e-9; acc[i][1] = i * 1e-9; }
-    const double x = 1.0 + threadIdx.x * 1e-12, y = 1.0 - threadIdx.x * 1e-12;
-    if (kind == 0) {
-        for (int it = 0; it < iters; ++it) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dmma(acc[i], x, y);
-        }
-    } else {
-        for (int it = 0; it < iters; ++it) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { acc[i][0] = fma(acc[i][0], x, y); acc[i][1] = fma(acc[i][1], y, x); }
-        }
-    }
-    double s = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += acc[i][0] + acc[i][1];
-    if (s == 123.456) sink[0] = s;
 }
 
 }  // namespace wd
