@@ -87,7 +87,7 @@ __device__ __forceinline__ void k2_mainloop(double (&acc)[2][2][GMAX][2][HALF ? 
         for (int ai = 0; ai < 2; ++ai) { n_ta[ai] = tA[ai * t8 + kbeg]; n_tb[ai] = tB[ai * t8 + kbeg]; }
 #pragma unroll
         for (int g = 0; g < GC; ++g) { n_be[g] = ub[g * gs + kbeg]; n_bo[g] = ub[g * gs + ldu + kbeg]; }
-#pragma unroll 1
+#pragma unroll 2
         for (int k = kbeg; k < kend; k += 4) {
             double fa[2], fb[2], be[GC], bo[GC];
 #pragma unroll
@@ -116,6 +116,85 @@ __device__ __forceinline__ void k2_mainloop(double (&acc)[2][2][GMAX][2][HALF ? 
     }
 }
 
+// Epilogue of one mirror target: stage the warp's 16 x span tile through shared memory, then store whole
+// columns segments (256 contiguous bytes per instruction; 512 for complex D).
+//   DESC = false: rows ascend with the quadrant row (targets (i,i') and (i,i'r));
+//   DESC = true : rows are the mirrored ones, written in ascending memory order ((ir,i'r) and (ir,i')).
+// val[ai][g][eo][h]: the butterfly-combined accumulators of this target.
+template <bool CPLX, bool DESC, int GMAX>
+__device__ __forceinline__ void k2_store_target(const K2Args &a, const K2Ctx &cx, const double (&val)[2][GMAX][2][2],
+                                                const int col, const int qbase, const int gcnt)
+{
+    const int N = cx.N, Q = cx.Q, i0 = cx.i0, zskip = cx.zskip, lane = cx.lane, r = cx.r, c = cx.c;
+    double *stg = cx.stg;
+    const int span = 16 * gcnt;
+    __syncwarp();
+#pragma unroll
+    for (int ai = 0; ai < 2; ++ai) {
+#pragma unroll
+        for (int g = 0; g < GMAX; ++g) {
+            if (g < gcnt) {
+                // the lane owns rows 16g+4c .. 16g+4c+3 of the unit: (even tile, odd tile) interleaved
+                const double v0 = val[ai][g][0][0], v1 = val[ai][g][1][0], v2 = val[ai][g][0][1], v3 = val[ai][g][1][1];
+                if (!DESC) {
+                    double2 *dst = reinterpret_cast<double2 *>(stg + (ai * 8 + r) * K2_STG_LD + 16 * g + 4 * c);
+                    dst[0] = make_double2(v0, v1);
+                    dst[1] = make_double2(v2, v3);
+                } else {
+                    double2 *dst = reinterpret_cast<double2 *>(stg + (ai * 8 + r) * K2_STG_LD + (span - 4) - 16 * g - 4 * c);
+                    dst[0] = make_double2(v3, v2);
+                    dst[1] = make_double2(v1, v0);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    // staging position s <-> global row: ascending i0+qbase+s ; descending (N-1-i0-qbase-(span-1)) + s
+    const int row0 = DESC ? (N - 1 - i0 - qbase - (span - 1)) : (i0 + qbase);
+    const int nrows = (int)min((long long)K2_ANG, a.nb - cx.b0);
+    const size_t mstride = (size_t)N * N * (CPLX ? 2 : 1);
+#pragma unroll 1
+    for (int hh = 0; hh * 32 < span; ++hh) {
+        const int s = hh * 32 + lane;
+        const int qm = DESC ? (qbase + span - 1 - s) : (qbase + s);
+        if (s >= span || qm >= Q || (DESC && qm < zskip)) continue;
+        const int row = row0 + s;
+        unsigned sgn = sigma_bit(row - col);                      // sigma(i - i')
+        unsigned keep = 0xffffffffu;
+        if (a.equator && zskip) {
+            const int j = cx.twoj >> 1;
+            if ((col == j && (row & 1)) || (row == j && (col & 1))) { keep = 0u; sgn = 0u; }   // exact zeros of :230-237
+        }
+        const double *src = stg + s;
+        double *dst = a.out + ((size_t)cx.b0 * N * N + (size_t)col * N + row) * (CPLX ? 2 : 1);
+        if (!CPLX) {
+#pragma unroll 4
+            for (int ar = 0; ar < nrows; ++ar) {
+                const double v = src[ar * K2_STG_LD];
+                dst[ar * mstride] = __hiloint2double((__double2hiint(v) ^ (int)sgn) & (int)keep, __double2loint(v) & (int)keep);
+            }
+        } else {
+            // exp(-i(m alpha + n gamma)) = (ca - i sa)(cg - i sg); m -> -m flips sa, n -> -n flips sg
+            const bool mneg = row < i0, nneg = col < i0;
+            const int qr = mneg ? (N - 1 - row - i0) : (row - i0);
+            const int qc = nneg ? (N - 1 - col - i0) : (col - i0);
+            const double *pa = cx.sPh + qr, *pg = cx.sPh + 2 * K2_ANG * Q + qc;
+#pragma unroll 2
+            for (int ar = 0; ar < nrows; ++ar) {
+                double v = src[ar * K2_STG_LD];
+                v = __hiloint2double((__double2hiint(v) ^ (int)sgn) & (int)keep, __double2loint(v) & (int)keep);
+                const double ca = pa[ar * Q], cg = pg[ar * Q];
+                double sa = pa[(K2_ANG + ar) * Q], sg = pg[(K2_ANG + ar) * Q];
+                if (mneg) sa = -sa;
+                if (nneg) sg = -sg;
+                const double cr = ca * cg - sa * sg;
+                const double ci = -(sa * cg + ca * sg);
+                *reinterpret_cast<double2 *>(dst + ar * mstride) = make_double2(v * cr, v * ci);
+            }
+        }
+    }
+}
+
 // One warp unit: quadrant column qn, gcnt groups of 16 quadrant rows starting at group g0, 16 angles.
 template <bool HALF, bool CPLX>
 __device__ __forceinline__ void k2_unit(const K2Args &a, const K2Ctx &cx, const int qn, const int g0, const int gcnt)
@@ -138,93 +217,28 @@ __device__ __forceinline__ void k2_unit(const K2Args &a, const K2Ctx &cx, const 
         }
     }
 
-    // ---- epilogue: butterfly, signs, stage through shared memory, coalesced stores ------------------
-    const int N = cx.N, Q = cx.Q, i0 = cx.i0, zskip = cx.zskip, lane = cx.lane, r = cx.r, c = cx.c;
-    double *stg = cx.stg;
-    const int ip = i0 + qn, ipr = N - 1 - ip;
+    // ---- epilogue ---------------------------------------------------------------------------------------
+    // butterfly, once: sum = P0 + P1 (targets (i,i'), (ir,i'r)), dif = P0 - P1 (targets (ir,i'), (i,i'r));
+    // for half-integer j the mirrored pair uses the accumulators of the other trig function (alt).
+    double vs[2][GMAX][2][2], vd[2][GMAX][2][2];
+#pragma unroll
+    for (int ai = 0; ai < 2; ++ai)
+#pragma unroll
+        for (int g = 0; g < GMAX; ++g)
+#pragma unroll
+            for (int eo = 0; eo < 2; ++eo)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    vs[ai][g][eo][h] = acc[0][ai][g][eo][0][h] + acc[1][ai][g][eo][0][h];
+                    vd[ai][g][eo][h] = acc[0][ai][g][eo][NALT - 1][h] - acc[1][ai][g][eo][NALT - 1][h];
+                }
+    const int ip = cx.i0 + qn, ipr = cx.N - 1 - ip;
     const int qbase = 16 * g0;                     // first quadrant row of the unit
-    const int span = 16 * gcnt;                    // rows covered (<= 64)
-#pragma unroll 1
-    for (int tgt = 0; tgt < 4; ++tgt) {
-        // tgt 0: ( i, i')  sum   ascending      tgt 1: (ir, i'r) sum  descending
-        // tgt 2: (ir, i')  dif   descending     tgt 3: ( i, i'r) dif  ascending
-        const bool desc = (tgt == 1) || (tgt == 2);
-        const bool dif = tgt >= 2;
-        const int col = (tgt & 1) ? ipr : ip;
-        if ((tgt & 1) && qn < zskip) continue;     // n = 0 mirrors onto itself (warp-uniform)
-        // global row of staging position s: ascending i0+qbase+s ; descending (N-1-i0-qbase-(span-1)) + s
-        const int row0 = desc ? (N - 1 - i0 - qbase - (span - 1)) : (i0 + qbase);
-        // sign sigma(di): di of the lane's element t is +-(i0+qbase+16g+4c+t) - col; only di mod 4 matters
-        const int dib = desc ? (N - 1 - i0 - qbase - col) : (i0 + qbase - col);
-        const int dstep = desc ? -1 : 1;
-        const unsigned difbit = dif ? 0x80000000u : 0u;
-        __syncwarp();
-#pragma unroll
-        for (int ai = 0; ai < 2; ++ai) {
-#pragma unroll
-            for (int g = 0; g < GMAX; ++g) {
-                if (g < gcnt) {
-                    double v[4];
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const int eo = t & 1, h = t >> 1;
-                        double p0 = acc[0][ai][g][eo][0][h], p1 = acc[1][ai][g][eo][0][h];
-                        if (HALF && dif) { p0 = acc[0][ai][g][eo][NALT - 1][h]; p1 = acc[1][ai][g][eo][NALT - 1][h]; }
-                        v[t] = flip(p0 + flip(p1, difbit), sigma_bit(dib + dstep * t));
-                    }
-                    const int pos = desc ? (span - 4) - 16 * g - 4 * c : 16 * g + 4 * c;
-                    double2 *dst = reinterpret_cast<double2 *>(stg + (ai * 8 + r) * K2_STG_LD + pos);
-                    dst[0] = desc ? make_double2(v[3], v[2]) : make_double2(v[0], v[1]);
-                    dst[1] = desc ? make_double2(v[1], v[0]) : make_double2(v[2], v[3]);
-                }
-            }
-        }
-        __syncwarp();
-        const int nrows = (int)min((long long)K2_ANG, a.nb - cx.b0);
-        const size_t colbase = (size_t)col * N + row0;
-#pragma unroll 1
-        for (int hh = 0; hh * 32 < span; ++hh) {
-            const int s = hh * 32 + lane;
-            const int qm = desc ? (qbase + span - 1 - s) : (qbase + s);
-            const bool ok = (s < span) && (qm < Q) && !(desc && qm < zskip);
-            const int row = row0 + s;
-            bool zero = false;
-            if (a.equator && zskip) {
-                const int j = cx.twoj >> 1;
-                zero = (col == j && (row & 1)) || (row == j && (col & 1));
-            }
-            int qr = 0, qc = 0;
-            bool mneg = false;
-            if (CPLX) {
-                mneg = row < i0;
-                qr = mneg ? (N - 1 - row - i0) : (row - i0);
-                qc = (col >= i0) ? (col - i0) : (N - 1 - col - i0);
-                if (!ok) qr = 0;
-            }
-            if (!ok) continue;
-            const double *src = stg + s;
-            double *dst = a.out + ((size_t)cx.b0 * N * N + colbase + s) * (CPLX ? 2 : 1);
-            const size_t mstride = (size_t)N * N * (CPLX ? 2 : 1);
-#pragma unroll 4
-            for (int ar = 0; ar < nrows; ++ar) {
-                double v = src[ar * K2_STG_LD];
-                if (zero) v = 0.0;
-                if (!CPLX) {
-                    dst[ar * mstride] = v;
-                } else {
-                    // exp(-i(m alpha + n gamma)) = (ca - i sa)(cg - i sg); m -> -m flips sa, n -> -n flips sg
-                    const double ca = cx.sPh[(0 * K2_ANG + ar) * Q + qr];
-                    double sa = cx.sPh[(1 * K2_ANG + ar) * Q + qr];
-                    const double cg = cx.sPh[(2 * K2_ANG + ar) * Q + qc];
-                    double sg = cx.sPh[(3 * K2_ANG + ar) * Q + qc];
-                    if (mneg) sa = -sa;
-                    if (col < i0) sg = -sg;
-                    const double cr = ca * cg - sa * sg;
-                    const double ci = -(sa * cg + ca * sg);
-                    *reinterpret_cast<double2 *>(dst + ar * mstride) = make_double2(v * cr, v * ci);
-                }
-            }
-        }
+    k2_store_target<CPLX, false, GMAX>(a, cx, vs, ip, qbase, gcnt);                 // ( i, i')
+    k2_store_target<CPLX, true, GMAX>(a, cx, vd, ip, qbase, gcnt);                  // (ir, i')
+    if (qn >= cx.zskip) {                          // n = 0 mirrors onto itself (warp-uniform)
+        k2_store_target<CPLX, true, GMAX>(a, cx, vs, ipr, qbase, gcnt);             // (ir, i'r)
+        k2_store_target<CPLX, false, GMAX>(a, cx, vd, ipr, qbase, gcnt);            // ( i, i'r)
     }
 }
 
