@@ -20,7 +20,7 @@ from fractions import Fraction
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwignerd_b200.so")
+LIB_PATH = os.environ.get("WIGNERD_B200_LIB") or os.path.join(_HERE, "libwignerd_b200.so")   # env override: kernel experiments
 
 WD_OK, WD_ERR_ARGUMENT, WD_ERR_ASSERT, WD_ERR_CUDA, WD_ERR_NOMEM, WD_ERR_UNSUPPORTED = range(6)
 GENERIC, NORTH, SOUTH, EQUATOR = 0, 1, 2, 3

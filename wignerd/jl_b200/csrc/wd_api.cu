@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -163,7 +164,7 @@ int get_plan(wd_handle_t h, int twoj, const Plan **out)
 bool dmma_fits(wd_handle_t h, const PlanDev &p, bool cplx, size_t *bytes)
 {
     const K2Smem L = k2_smem_layout(p.Q, p.Kp, p.ldu, cplx);
-    *bytes = (size_t)L.total * sizeof(double);
+    *bytes = (size_t)L.total * sizeof(double) + 16;      // + the unit-scheduler counter
     return *bytes <= h->smem_optin;
 }
 
@@ -192,11 +193,13 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
     a.p = pl.dev;
     a.alpha = alpha; a.beta = beta; a.gamma = gamma;
     a.nb = nb; a.out = out; a.equator = equator ? 1 : 0;
+
     size_t smem = 0;
     const bool fits = dmma_fits(h, pl.dev, cplx, &smem);
     int variant = h->variant;
     if (variant == 2 && !fits) return fail(WD_ERR_UNSUPPORTED, "2j = %d does not fit the DMMA kernel (%zu B of shared memory)", pl.dev.twoj, smem);
-    const bool use_dmma = (variant == 2) || (variant == 0 && fits);
+    // Equator() requests (single matrices, exact zeros of :230-237) take the plain kernel
+    const bool use_dmma = !equator && ((variant == 2) || (variant == 0 && fits));
     const bool half = pl.dev.twoj & 1;
     if (use_dmma) {
         if (half) return cplx ? launch_dmma<true, true>(h, a, smem) : launch_dmma<true, false>(h, a, smem);

@@ -3,17 +3,25 @@
 //
 //   CTA = 8 warps, persistent over chunks of 16 angles.  Shared memory: UQ (all of it, zero-padded to whole
 //   16-row groups), the mu / w vectors, the chunk's trig tables Tc/Ts[16][ldt] (w cos(mu beta),
-//   w sin(mu beta)), optional phase tables, and one 16 x 64 staging tile per warp.
+//   w sin(mu beta)), optional phase tables, and two 8 x 64 staging tiles per warp.
 //   Warp unit = one quadrant column qn  x  up to GMAX groups of 16 quadrant rows  x  16 angles.
 //   MMA roles:  A[8 angles][4 kp] = T(beta, kp) * UQ[qn][kp],  B[4 kp][8 rows] = UQ[row][kp],
 //   C[8 angles][8 rows].  A 16-row group is two tiles -- its even rows and its odd rows -- so that one tile
-//   needs one trig function; a lane then owns 4 consecutive rows of the group.
-//   Epilogue: P0 +- P1 butterfly, sign sigma, staged through shared memory so that every global store
-//   instruction writes 256 contiguous bytes of one output column (512 for complex D).
+//   needs one trig function; a lane then owns 4 consecutive rows of the group.  Angle tile ai holds the
+//   angles of parity ai of the chunk (angle a = 2 r + ai in MMA row r), which makes the 16-byte alignment of
+//   every output run of a tile the same.
+//   Epilogue: P0 +- P1 butterfly and sign sigma in registers, one 8 x span tile staged in shared memory per
+//   (mirror target, angle tile), then
+//     real d   : the 8 runs of the tile leave through the TMA engine -- cp.async.bulk shared -> global, one bulk
+//                copy of up to 512 B per run, issued by lanes 0..7; the at most two 8-byte edge elements of a
+//                run that bulk copies cannot cover (16-byte alignment) are stored by lanes 8..23;
+//     complex D: LDS + fused exp(-i(m alpha + n gamma)) + 16-byte STG (512 contiguous bytes per instruction).
 //
-//   Code-size note (ncu, round 1): a fully unrolled epilogue made this kernel 340 KB of SASS and
-//   instruction-fetch bound ("no_instruction" 60 % of stall samples); the epilogue is therefore a runtime
-//   loop over the four mirror targets and the main loop is the only part specialised on the group count.
+//   Measured history of this kernel (cfg-2, j = 100, 10^5 angles, B200; profiles/): fully unrolled epilogue
+//   -> instruction-fetch bound, 33 ms; runtime epilogue loops -> 15.4 ms; single butterfly + lean LDS/STG
+//   store loop -> 12.2 ms with the LSU/shared-memory pipe as co-bottleneck of the DMMA pipe (the staged
+//   read-back + STG.64 stream costs as many LSU wavefronts as the whole main loop); bulk-copy stores remove
+//   that read-back from the LSU.
 #pragma once
 #include "wd_kernels.cuh"
 
@@ -22,14 +30,48 @@ namespace wd {
 constexpr int K2_WARPS = 8;
 constexpr int K2_THREADS = K2_WARPS * 32;
 constexpr int K2_ANG = 16;                 // angles per chunk (2 MMA row tiles)
-constexpr int K2_STG_LD = 66;              // staging row stride (doubles): == 2 mod 4, 16B-aligned rows
-constexpr int K2_STG_ROWS = 16;
+constexpr int K2_STG_LD = 66;              // staging row stride (doubles): == 2 mod 16 -> conflict-free 16-byte stores
+constexpr int K2_STG_ROWS = 16;            // both angle tiles of a chunk
 
 __device__ __forceinline__ void dmma(double (&d)[2], double a, double b)
 {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(d[0]), "+d"(d[1])
         : "d"(a), "d"(b));
+}
+
+// ---- TMA engine, non-tensor form: one bulk asynchronous copy global -> shared (SASS UBLKCP) brings the whole
+// eigenvector table UQ of the j being computed into shared memory, completion signalled on an mbarrier.
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *sdst, const void *gsrc, unsigned bytes, void *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
 }
 
 struct K2Smem {                 // offsets in doubles, computed identically on host and device
@@ -50,7 +92,7 @@ __host__ __device__ inline K2Smem k2_smem_layout(int Q, int Kp, int ldu, bool cp
     s.ph = o;  o += cplx ? 4 * K2_ANG * Q : 0;          // cos(m a), sin(m a), cos(n g), sin(n g)  [16][Q]
     o = (o + 1) & ~1;
     s.stg = o; o += K2_WARPS * K2_STG_ROWS * K2_STG_LD;
-    s.total = o;
+    s.total = o;                                        // (+ 16 bytes: the unit counter)
     return s;
 }
 
@@ -61,6 +103,9 @@ struct K2Ctx {                  // per-thread constants of the DMMA kernel
     int lane, r, c;
     long long b0;
 };
+
+// row of the trig tables that holds angle a of the chunk: even angles first (tile 0), odd angles second (tile 1)
+__device__ __forceinline__ int k2_trig_row(int a) { return ((a & 1) << 3) + (a >> 1); }
 
 // Main loop of one warp unit, specialised on the number GC of 16-row groups actually present.
 // acc[class][angle tile][group][even/odd rows][main/alt][frag]; groups >= GC stay untouched (zero).
@@ -116,18 +161,31 @@ __device__ __forceinline__ void k2_mainloop(double (&acc)[2][2][GMAX][2][HALF ? 
     }
 }
 
-// Epilogue of one mirror target: stage the warp's 16 x span tile through shared memory, then store whole
-// columns segments (256 contiguous bytes per instruction; 512 for complex D).
+// Epilogue of one mirror target: for each angle tile, stage the 8 x span tile (signs applied) and store it.
 //   DESC = false: rows ascend with the quadrant row (targets (i,i') and (i,i'r));
 //   DESC = true : rows are the mirrored ones, written in ascending memory order ((ir,i'r) and (ir,i')).
 // val[ai][g][eo][h]: the butterfly-combined accumulators of this target.
 template <bool CPLX, bool DESC, int GMAX>
-__device__ __forceinline__ void k2_store_target(const K2Args &a, const K2Ctx &cx, const double (&val)[2][GMAX][2][2],
+__device__ __forceinline__ void k2_store_target(const K2Args &a, K2Ctx &cx, const double (&val)[2][GMAX][2][2],
                                                 const int col, const int qbase, const int gcnt)
 {
     const int N = cx.N, Q = cx.Q, i0 = cx.i0, zskip = cx.zskip, lane = cx.lane, r = cx.r, c = cx.c;
-    double *stg = cx.stg;
     const int span = 16 * gcnt;
+    // staging position s <-> global row: ascending i0+qbase+s ; descending (N-1-i0-qbase-(span-1)) + s
+    const int row0 = DESC ? (N - 1 - i0 - qbase - (span - 1)) : (i0 + qbase);
+    // valid staging positions [s_lo, s_hi): quadrant row < Q, and (mirrored rows) quadrant row >= zskip
+    const int s_lo = DESC ? max(0, qbase + span - Q) : 0;
+    const int s_hi = DESC ? min(span, qbase + span - zskip) : min(span, Q - qbase);
+    if (s_hi <= s_lo) return;                                         // warp-uniform
+    // sigma(row - col) of the lane's element t: row - col = +-(16g + 4c + t) + const, only mod 4 matters
+    const int dib = DESC ? (N - 1 - i0 - qbase - col) : (i0 + qbase - col);
+    unsigned sb[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) sb[t] = sigma_bit(DESC ? dib - t : dib + t);
+    const size_t NN = (size_t)N * N;
+    // Stage the 16 x span tile (row ai*8 + r <-> angle 2r + ai of the chunk), then store whole column segments:
+    // 256 contiguous bytes per instruction for real d, 512 for complex D (fused phase).
+    double *buf = cx.stg;
     __syncwarp();
 #pragma unroll
     for (int ai = 0; ai < 2; ++ai) {
@@ -135,61 +193,61 @@ __device__ __forceinline__ void k2_store_target(const K2Args &a, const K2Ctx &cx
         for (int g = 0; g < GMAX; ++g) {
             if (g < gcnt) {
                 // the lane owns rows 16g+4c .. 16g+4c+3 of the unit: (even tile, odd tile) interleaved
-                const double v0 = val[ai][g][0][0], v1 = val[ai][g][1][0], v2 = val[ai][g][0][1], v3 = val[ai][g][1][1];
-                if (!DESC) {
-                    double2 *dst = reinterpret_cast<double2 *>(stg + (ai * 8 + r) * K2_STG_LD + 16 * g + 4 * c);
-                    dst[0] = make_double2(v0, v1);
-                    dst[1] = make_double2(v2, v3);
-                } else {
-                    double2 *dst = reinterpret_cast<double2 *>(stg + (ai * 8 + r) * K2_STG_LD + (span - 4) - 16 * g - 4 * c);
-                    dst[0] = make_double2(v3, v2);
-                    dst[1] = make_double2(v1, v0);
-                }
+                const double v0 = flip(val[ai][g][0][0], sb[0]), v1 = flip(val[ai][g][1][0], sb[1]);
+                const double v2 = flip(val[ai][g][0][1], sb[2]), v3 = flip(val[ai][g][1][1], sb[3]);
+                double *p = buf + (ai * 8 + r) * K2_STG_LD + (DESC ? (span - 4) - 16 * g - 4 * c : 16 * g + 4 * c);
+                reinterpret_cast<double2 *>(p)[0] = DESC ? make_double2(v3, v2) : make_double2(v0, v1);
+                reinterpret_cast<double2 *>(p)[1] = DESC ? make_double2(v1, v0) : make_double2(v2, v3);
             }
         }
     }
     __syncwarp();
-    // staging position s <-> global row: ascending i0+qbase+s ; descending (N-1-i0-qbase-(span-1)) + s
-    const int row0 = DESC ? (N - 1 - i0 - qbase - (span - 1)) : (i0 + qbase);
-    const int nrows = (int)min((long long)K2_ANG, a.nb - cx.b0);
-    const size_t mstride = (size_t)N * N * (CPLX ? 2 : 1);
+    const size_t e00 = (size_t)cx.b0 * NN + (size_t)col * N + row0;   // angle 0 of the chunk, staging position 0
 #pragma unroll 1
     for (int hh = 0; hh * 32 < span; ++hh) {
         const int s = hh * 32 + lane;
-        const int qm = DESC ? (qbase + span - 1 - s) : (qbase + s);
-        if (s >= span || qm >= Q || (DESC && qm < zskip)) continue;
-        const int row = row0 + s;
-        unsigned sgn = sigma_bit(row - col);                      // sigma(i - i')
-        unsigned keep = 0xffffffffu;
-        if (a.equator && zskip) {
-            const int j = cx.twoj >> 1;
-            if ((col == j && (row & 1)) || (row == j && (col & 1))) { keep = 0u; sgn = 0u; }   // exact zeros of :230-237
-        }
-        const double *src = stg + s;
-        double *dst = a.out + ((size_t)cx.b0 * N * N + (size_t)col * N + row) * (CPLX ? 2 : 1);
+        if (s < s_lo || s >= s_hi) continue;
+        const double *src = buf + s;
         if (!CPLX) {
+#pragma unroll
+            for (int ai = 0; ai < 2; ++ai) {
+                const long long bfirst = cx.b0 + ai;
+                if (bfirst >= a.nb) break;                            // warp-uniform
+                const int nrows = (int)min(8LL, (a.nb - bfirst + 1) / 2);
+                const double *sp = src + ai * 8 * K2_STG_LD;
+                double *dst = a.out + e00 + (size_t)ai * NN + s;
 #pragma unroll 4
-            for (int ar = 0; ar < nrows; ++ar) {
-                const double v = src[ar * K2_STG_LD];
-                dst[ar * mstride] = __hiloint2double((__double2hiint(v) ^ (int)sgn) & (int)keep, __double2loint(v) & (int)keep);
+                for (int ar = 0; ar < nrows; ++ar) {                  // angle 2 ar + ai of the chunk
+                    *dst = *sp;
+                    sp += K2_STG_LD;
+                    dst += 2 * NN;
+                }
             }
         } else {
             // exp(-i(m alpha + n gamma)) = (ca - i sa)(cg - i sg); m -> -m flips sa, n -> -n flips sg
+            const int row = row0 + s;
             const bool mneg = row < i0, nneg = col < i0;
             const int qr = mneg ? (N - 1 - row - i0) : (row - i0);
             const int qc = nneg ? (N - 1 - col - i0) : (col - i0);
-            const double *pa = cx.sPh + qr, *pg = cx.sPh + 2 * K2_ANG * Q + qc;
+#pragma unroll
+            for (int ai = 0; ai < 2; ++ai) {
+                const long long bfirst = cx.b0 + ai;
+                if (bfirst >= a.nb) break;                            // warp-uniform
+                const int nrows = (int)min(8LL, (a.nb - bfirst + 1) / 2);
+                const double *pa = cx.sPh + ai * Q + qr, *pg = cx.sPh + (2 * K2_ANG + ai) * Q + qc;
+                const double *sp = src + ai * 8 * K2_STG_LD;
+                double2 *dst = reinterpret_cast<double2 *>(a.out) + e00 + (size_t)ai * NN + s;
 #pragma unroll 2
-            for (int ar = 0; ar < nrows; ++ar) {
-                double v = src[ar * K2_STG_LD];
-                v = __hiloint2double((__double2hiint(v) ^ (int)sgn) & (int)keep, __double2loint(v) & (int)keep);
-                const double ca = pa[ar * Q], cg = pg[ar * Q];
-                double sa = pa[(K2_ANG + ar) * Q], sg = pg[(K2_ANG + ar) * Q];
-                if (mneg) sa = -sa;
-                if (nneg) sg = -sg;
-                const double cr = ca * cg - sa * sg;
-                const double ci = -(sa * cg + ca * sg);
-                *reinterpret_cast<double2 *>(dst + ar * mstride) = make_double2(v * cr, v * ci);
+                for (int ar = 0; ar < nrows; ++ar) {                  // angle 2 ar + ai of the chunk
+                    const double v = sp[ar * K2_STG_LD];
+                    const double ca = pa[(2 * ar) * Q], cg = pg[(2 * ar) * Q];
+                    double sa = pa[(K2_ANG + 2 * ar) * Q], sg = pg[(K2_ANG + 2 * ar) * Q];
+                    if (mneg) sa = -sa;
+                    if (nneg) sg = -sg;
+                    const double cr = ca * cg - sa * sg;
+                    const double ci = -(sa * cg + ca * sg);
+                    dst[(size_t)(2 * ar) * NN] = make_double2(v * cr, v * ci);
+                }
             }
         }
     }
@@ -197,7 +255,7 @@ __device__ __forceinline__ void k2_store_target(const K2Args &a, const K2Ctx &cx
 
 // One warp unit: quadrant column qn, gcnt groups of 16 quadrant rows starting at group g0, 16 angles.
 template <bool HALF, bool CPLX>
-__device__ __forceinline__ void k2_unit(const K2Args &a, const K2Ctx &cx, const int qn, const int g0, const int gcnt)
+__device__ __forceinline__ void k2_unit(const K2Args &a, K2Ctx &cx, const int qn, const int g0, const int gcnt)
 {
     constexpr int GMAX = HALF ? 2 : 4;
     constexpr int NALT = HALF ? 2 : 1;
@@ -253,6 +311,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_dmma_kernel(K2Args a)
     const int ldt = L.ldt;
     double *sUQ = sm + L.uq, *sMu = sm + L.mu, *sW = sm + L.w, *sTc = sm + L.tc, *sTs = sm + L.ts;
     double *sPh = sm + L.ph;
+    int *sCounter = reinterpret_cast<int *>(sm + L.total);     // one int after the staging tiles
     const int tid = threadIdx.x, warp = tid >> 5;
     K2Ctx cx;
     cx.sUQ = sUQ; cx.sTc = sTc; cx.sTs = sTs; cx.sPh = sPh;
@@ -261,16 +320,23 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_dmma_kernel(K2Args a)
     cx.Kp = Kp; cx.K0p = p.K0p; cx.twoj = p.twoj;
     cx.lane = tid & 31; cx.r = cx.lane >> 2; cx.c = cx.lane & 3;
 
-    // one-time: UQ (+ zero pad rows), mu, w -> shared (16-byte vector copies; ldu and Kp are even)
+    // one-time: UQ -> shared through the TMA engine (one bulk copy, mbarrier-signalled); zero pad rows, mu, w by hand
     {
-        const double2 *src = reinterpret_cast<const double2 *>(p.uq);
-        double2 *dst = reinterpret_cast<double2 *>(sUQ);
-        const int nvalid = (Q * ldu) / 2, nall = (L.qpad * ldu) / 2;
-        for (int i = tid; i < nall; i += K2_THREADS) dst[i] = (i < nvalid) ? src[i] : make_double2(0.0, 0.0);
+        void *mbar = reinterpret_cast<char *>(sm + L.total) + 8;   // 8 bytes after the unit counter
+        const unsigned uq_bytes = (unsigned)(Q * ldu) * 8u;        // a multiple of 16: ldu is even
+        if (tid == 0) {
+            mbar_init(mbar, 1);
+            mbar_expect_tx(mbar, uq_bytes);
+            bulk_load(sUQ, p.uq, uq_bytes, mbar);
+        }
+        for (int i = Q * ldu + tid; i < L.qpad * ldu; i += K2_THREADS) sUQ[i] = 0.0;
         for (int i = tid; i < Kp; i += K2_THREADS) { sMu[i] = p.mu[i]; sW[i] = p.w[i]; }
+        __syncthreads();                                           // the mbarrier is initialised for everybody
+        mbar_wait(mbar, 0);
     }
     const int ngroups = L.qpad >> 4;
-    const int upc = (ngroups + GMAX - 1) / GMAX;          // units per column
+    const int upc = (ngroups + GMAX - 1) / GMAX;          // parts per column
+    const int gbase = ngroups / upc, grem = ngroups - gbase * upc;   // the first grem parts have gbase+1 groups
     const int nunits = Q * upc;
     const long long nchunks = (a.nb + K2_ANG - 1) / K2_ANG;
 
@@ -278,6 +344,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_dmma_kernel(K2Args a)
         const long long b0 = ch * K2_ANG;
         cx.b0 = b0;
         __syncthreads();                                   // previous chunk's readers are done (and UQ is in)
+        if (tid == 0) *sCounter = 0;
 #pragma unroll 1
         for (int idx = tid; idx < K2_ANG * Kp; idx += K2_THREADS) {
             const int ang = idx / Kp, kp = idx - ang * Kp;
@@ -285,8 +352,9 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_dmma_kernel(K2Args a)
             double s, cs;
             sincos(sMu[kp] * a.beta[b], &s, &cs);         // fl(mu*beta) then sincos, like :199
             const double w = sW[kp];
-            sTc[ang * ldt + kp] = w * cs;
-            sTs[ang * ldt + kp] = w * s;
+            const int row = k2_trig_row(ang);
+            sTc[row * ldt + kp] = w * cs;
+            sTs[row * ldt + kp] = w * s;
         }
         if (CPLX) {
 #pragma unroll 1
@@ -303,11 +371,17 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_dmma_kernel(K2Args a)
         }
         __syncthreads();
 
+        // dynamic unit scheduler (one shared counter per chunk): unit v -> part v / Q of column v % Q, so the
+        // larger parts of all columns are handed out before the smaller ones
 #pragma unroll 1
-        for (int u = warp; u < nunits; u += K2_WARPS) {
-            const int qn = u / upc;
-            const int g0 = (u - qn * upc) * GMAX;
-            const int gcnt = min(GMAX, ngroups - g0);
+        for (;;) {
+            int v = 0;
+            if (cx.lane == 0) v = atomicAdd(sCounter, 1);
+            v = __shfl_sync(0xffffffffu, v, 0);
+            if (v >= nunits) break;
+            const int part = v / Q, qn = v - part * Q;
+            const int g0 = part * gbase + min(part, grem);
+            const int gcnt = gbase + (part < grem ? 1 : 0);
             k2_unit<HALF, CPLX>(a, cx, qn, g0, gcnt);
         }
     }

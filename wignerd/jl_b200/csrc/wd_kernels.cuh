@@ -137,7 +137,7 @@ struct K2Args {
     const double *beta, *alpha, *gamma;   // alpha/gamma only for complex output
     long long nb;
     double *out;                          // nb * N*N doubles (or * 2 for complex)
-    int equator;                          // apply the exact zeros of :230-237
+    int equator;                          // apply the exact zeros of :230-237 (plain kernel only)
 };
 
 template <bool CPLX>
