@@ -164,7 +164,7 @@ int get_plan(wd_handle_t h, int twoj, const Plan **out)
 bool dmma_fits(wd_handle_t h, const PlanDev &p, bool cplx, size_t *bytes)
 {
     const K2Smem L = k2_smem_layout(p.Q, p.Kp, p.ldu, cplx);
-    *bytes = (size_t)L.total * sizeof(double) + 16;      // + the unit-scheduler counter
+    *bytes = (size_t)L.total * sizeof(double);
     return *bytes <= h->smem_optin;
 }
 
@@ -178,7 +178,7 @@ int launch_dmma(wd_handle_t h, const K2Args &a, size_t smem)
     }
     const long long nchunks = (a.nb + K2_ANG - 1) / K2_ANG;
     const int grid = (int)std::min<long long>(nchunks, h->num_sms);
-    k2_dmma_kernel<HALF, CPLX><<<grid, K2_THREADS, smem, h->stream>>>(a);
+    k2_dmma_kernel<HALF, CPLX><<<grid, k2_threads(CPLX), smem, h->stream>>>(a);
     h->launches++;
     CU(cudaGetLastError());
     return WD_OK;
@@ -193,7 +193,6 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
     a.p = pl.dev;
     a.alpha = alpha; a.beta = beta; a.gamma = gamma;
     a.nb = nb; a.out = out; a.equator = equator ? 1 : 0;
-
     size_t smem = 0;
     const bool fits = dmma_fits(h, pl.dev, cplx, &smem);
     int variant = h->variant;

@@ -1,37 +1,42 @@
 // wd_k2_dmma.cuh -- the hot kernel: batched d^j(beta) / D^j(alpha,beta,gamma) contraction on the FP64
 // tensor pipe (mma.sync m8n8k4 f64 -> SASS DMMA.8x8x4, the only FP64 tensor path on sm_100a).
 //
-//   CTA = 8 warps, persistent over chunks of 16 angles.  Shared memory: UQ (all of it, zero-padded to whole
-//   16-row groups), the mu / w vectors, the chunk's trig tables Tc/Ts[16][ldt] (w cos(mu beta),
-//   w sin(mu beta)), optional phase tables, and two 8 x 64 staging tiles per warp.
+//   CTA, persistent over chunks of 16 angles:
+//     real d   : 12 warps, warp-specialised -- 8 COMPUTE warps (two warpgroups, 208 registers after
+//                setmaxnreg.inc) and 4 STORE warps (one warpgroup, 56 registers after setmaxnreg.dec);
+//     complex D: 8 warps that do both jobs (the store needs the per-chunk phase tables).
+//   Shared memory: UQ (all of it, one TMA bulk copy, zero-padded to whole 16-row groups), the mu / w vectors, the
+//   chunk's trig tables Tc/Ts[16][ldt] (w cos(mu beta), w sin(mu beta)), optional phase tables, and one 16 x 64
+//   staging tile + descriptor + full/empty mbarrier pair per compute warp.
 //   Warp unit = one quadrant column qn  x  up to GMAX groups of 16 quadrant rows  x  16 angles.
 //   MMA roles:  A[8 angles][4 kp] = T(beta, kp) * UQ[qn][kp],  B[4 kp][8 rows] = UQ[row][kp],
 //   C[8 angles][8 rows].  A 16-row group is two tiles -- its even rows and its odd rows -- so that one tile
 //   needs one trig function; a lane then owns 4 consecutive rows of the group.  Angle tile ai holds the
-//   angles of parity ai of the chunk (angle a = 2 r + ai in MMA row r), which makes the 16-byte alignment of
-//   every output run of a tile the same.
-//   Epilogue: P0 +- P1 butterfly and sign sigma in registers, one 8 x span tile staged in shared memory per
-//   (mirror target, angle tile), then
-//     real d   : the 8 runs of the tile leave through the TMA engine -- cp.async.bulk shared -> global, one bulk
-//                copy of up to 512 B per run, issued by lanes 0..7; the at most two 8-byte edge elements of a
-//                run that bulk copies cannot cover (16-byte alignment) are stored by lanes 8..23;
-//     complex D: LDS + fused exp(-i(m alpha + n gamma)) + 16-byte STG (512 contiguous bytes per instruction).
+//   angles of parity ai of the chunk (angle a = 2 r + ai in MMA row r).
+//   Epilogue (compute warp): butterfly P0 +- P1, sign sigma, and for each of the four mirror targets the
+//   16 x span tile is written to the warp's staging buffer (conflict-free 16-byte STS) and handed to a store
+//   warp through the full/empty mbarriers.  Store warp: drains tiles of its two compute warps -- every store
+//   instruction writes 256 contiguous bytes of one output column (partial-sector writes are what the L2 cannot
+//   absorb: direct register stores of the same data ran this kernel at 17-19 ms).
 //
-//   Measured history of this kernel (cfg-2, j = 100, 10^5 angles, B200; profiles/): fully unrolled epilogue
-//   -> instruction-fetch bound, 33 ms; runtime epilogue loops -> 15.4 ms; single butterfly + lean LDS/STG
-//   store loop -> 12.2 ms with the LSU/shared-memory pipe as co-bottleneck of the DMMA pipe (the staged
-//   read-back + STG.64 stream costs as many LSU wavefronts as the whole main loop); bulk-copy stores remove
-//   that read-back from the LSU.
+//   Why warp specialisation (ncu + experiment builds, profiles/): with 8 symmetric warps the drain loop --
+//   ~1100 dependent integer/LDS/STG instructions per unit, ~5 cycles each with only two warps per scheduler --
+//   kept every warp out of its main loop for ~45 % of the time (12.1 ms at cfg-2); without the drain the same
+//   kernel runs in 8.9 ms.  Moving the drain to otherwise idle warps lets the compute warps return to the DMMA
+//   pipe after ~600 instructions.
 #pragma once
 #include "wd_kernels.cuh"
 
 namespace wd {
 
-constexpr int K2_WARPS = 8;
-constexpr int K2_THREADS = K2_WARPS * 32;
+constexpr int K2_CWARPS = 8;               // compute warps
+constexpr int K2_SWARPS = 8;               // store warps, one per compute warp (real-d kernels only)
 constexpr int K2_ANG = 16;                 // angles per chunk (2 MMA row tiles)
 constexpr int K2_STG_LD = 66;              // staging row stride (doubles): == 2 mod 16 -> conflict-free 16-byte stores
 constexpr int K2_STG_ROWS = 16;            // both angle tiles of a chunk
+constexpr int K2_REGS_COMPUTE = 208;
+constexpr int K2_REGS_STORE = 48;             // 8*32*208 + 8*32*48 = 65536 = the whole register file
+__host__ __device__ constexpr int k2_threads(bool cplx) { return (K2_CWARPS + (cplx ? 0 : K2_SWARPS)) * 32; }
 
 __device__ __forceinline__ void dmma(double (&d)[2], double a, double b)
 {
@@ -40,17 +45,21 @@ __device__ __forceinline__ void dmma(double (&d)[2], double a, double b)
         : "d"(a), "d"(b));
 }
 
-// ---- TMA engine, non-tensor form: one bulk asynchronous copy global -> shared (SASS UBLKCP) brings the whole
-// eigenvector table UQ of the j being computed into shared memory, completion signalled on an mbarrier.
+// ---- mbarriers, and the TMA engine in its non-tensor form: one bulk asynchronous copy global -> shared (SASS
+// UBLKCP) brings the whole eigenvector table UQ of the j being computed into shared memory.
 __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(void *bar, unsigned count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
 __device__ __forceinline__ void bulk_load(void *sdst, const void *gsrc, unsigned bytes, void *bar)
 {
@@ -59,23 +68,41 @@ __device__ __forceinline__ void bulk_load(void *sdst, const void *gsrc, unsigned
                  "l"(gsrc), "r"(bytes), "r"(smem_addr(bar))
                  : "memory");
 }
-__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
+__device__ __forceinline__ bool mbar_test(void *bar, unsigned parity)
 {
+    unsigned ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_addr(bar)),
-        "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity)
         : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
+{
+    while (!mbar_test(bar, parity)) { }
+}
+// named barrier (bar.sync is warp-aligned: the warp must be converged, hence the __syncwarp)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    __syncwarp();
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// what a store warp needs to know about a staged tile
+struct K2Desc {
+    unsigned long long e00;     // element index of (angle 0 of the chunk, staging position 0)
+    int s_lo, s_hi;             // valid staging positions; s_hi < 0: the compute warp has finished
+    int nrows0, nrows1;         // existing angles of tile 0 (even angles) / tile 1 (odd angles)
+    int pad[2];
+};
+
 struct K2Smem {                 // offsets in doubles, computed identically on host and device
-    int uq, mu, w, tc, ts, ph, stg, total;
+    int uq, mu, w, tc, ts, ph, stg, desc, bars, total;
     int ldt, qpad;
 };
 __host__ __device__ inline K2Smem k2_smem_layout(int Q, int Kp, int ldu, bool cplx)
@@ -91,16 +118,21 @@ __host__ __device__ inline K2Smem k2_smem_layout(int Q, int Kp, int ldu, bool cp
     s.ts = o;  o += K2_ANG * s.ldt;
     s.ph = o;  o += cplx ? 4 * K2_ANG * Q : 0;          // cos(m a), sin(m a), cos(n g), sin(n g)  [16][Q]
     o = (o + 1) & ~1;
-    s.stg = o; o += K2_WARPS * K2_STG_ROWS * K2_STG_LD;
-    s.total = o;                                        // (+ 16 bytes: the unit counter)
+    s.stg = o;  o += K2_CWARPS * K2_STG_ROWS * K2_STG_LD;
+    s.desc = o; o += K2_CWARPS * (int)(sizeof(K2Desc) / 8);
+    s.bars = o; o += 2 * K2_CWARPS + 2;                 // full[8], empty[8], UQ-load barrier, unit counter
+    s.total = o;
     return s;
 }
 
-struct K2Ctx {                  // per-thread constants of the DMMA kernel
+struct K2Ctx {                  // per-thread constants of a compute warp
     const double *sUQ, *sTc, *sTs, *sPh;
     double *stg;
+    K2Desc *desc;
+    void *full, *empty;
     int ldu, ldt, N, Q, i0, zskip, Kp, K0p, twoj;
     int lane, r, c;
+    unsigned tiles;             // tiles handed to the store warp so far (mbarrier phase)
     long long b0;
 };
 
@@ -125,43 +157,78 @@ __device__ __forceinline__ void k2_mainloop(double (&acc)[2][2][GMAX][2][HALF ? 
     for (int cls = 0; cls < 2; ++cls) {
         const int kbeg = cls ? cx.K0p : 0;
         const int kend = cls ? cx.Kp : cx.K0p;
-        // software pipeline: fragments of step k+4 are loaded while the DMMAs of step k issue.  The
-        // prefetch of the step after the last one reads (and discards) in-bounds shared memory.
-        double n_un = un[kbeg], n_ta[2], n_tb[2], n_be[GC], n_bo[GC];
+        // Software pipeline with two explicit fragment sets (no register moves): while the 16 DMMAs of one k-step
+        // issue from set X, the loads of the next step land in set Y.  A load past the last step reads (and
+        // discards) in-bounds shared memory.
+        struct Frag { double un, ta[2], tb[2], be[GC], bo[GC]; };
+        auto load = [&](Frag &f, const int k) {
+            f.un = un[k];
 #pragma unroll
-        for (int ai = 0; ai < 2; ++ai) { n_ta[ai] = tA[ai * t8 + kbeg]; n_tb[ai] = tB[ai * t8 + kbeg]; }
+            for (int ai = 0; ai < 2; ++ai) { f.ta[ai] = tA[ai * t8 + k]; f.tb[ai] = tB[ai * t8 + k]; }
 #pragma unroll
-        for (int g = 0; g < GC; ++g) { n_be[g] = ub[g * gs + kbeg]; n_bo[g] = ub[g * gs + ldu + kbeg]; }
-#pragma unroll 2
-        for (int k = kbeg; k < kend; k += 4) {
-            double fa[2], fb[2], be[GC], bo[GC];
+            for (int g = 0; g < GC; ++g) { f.be[g] = ub[g * gs + k]; f.bo[g] = ub[g * gs + ldu + k]; }
+        };
+        auto step = [&](Frag &f) {
 #pragma unroll
-            for (int ai = 0; ai < 2; ++ai) { fa[ai] = n_ta[ai] * n_un; fb[ai] = n_tb[ai] * n_un; }
-#pragma unroll
-            for (int g = 0; g < GC; ++g) { be[g] = n_be[g]; bo[g] = n_bo[g]; }
-            const int kn = k + 4;
-            n_un = un[kn];
-#pragma unroll
-            for (int ai = 0; ai < 2; ++ai) { n_ta[ai] = tA[ai * t8 + kn]; n_tb[ai] = tB[ai * t8 + kn]; }
-#pragma unroll
-            for (int g = 0; g < GC; ++g) { n_be[g] = ub[g * gs + kn]; n_bo[g] = ub[g * gs + ldu + kn]; }
+            for (int ai = 0; ai < 2; ++ai) { f.ta[ai] *= f.un; f.tb[ai] *= f.un; }      // A = T(beta, kp) * UQ[qn][kp]
 #pragma unroll
             for (int g = 0; g < GC; ++g) {
 #pragma unroll
                 for (int ai = 0; ai < 2; ++ai) {
-                    dmma(acc[cls][ai][g][0][0], fa[ai], be[g]);
-                    dmma(acc[cls][ai][g][1][0], fb[ai], bo[g]);
+                    dmma(acc[cls][ai][g][0][0], f.ta[ai], f.be[g]);
+                    dmma(acc[cls][ai][g][1][0], f.tb[ai], f.bo[g]);
                     if (HALF) {
-                        dmma(acc[cls][ai][g][0][1], fb[ai], be[g]);
-                        dmma(acc[cls][ai][g][1][1], fa[ai], bo[g]);
+                        dmma(acc[cls][ai][g][0][1], f.tb[ai], f.be[g]);
+                        dmma(acc[cls][ai][g][1][1], f.ta[ai], f.bo[g]);
                     }
                 }
+            }
+        };
+        Frag f0, f1;
+        load(f0, kbeg);
+        int k = kbeg;
+#pragma unroll 1
+        for (; k + 4 < kend; k += 8) {
+            load(f1, k + 4);
+            step(f0);
+            load(f0, k + 8);
+            step(f1);
+        }
+        if (k < kend) step(f0);
+    }
+}
+
+// Drain of one staged 16 x span tile of real d: 256 contiguous bytes per store instruction.
+// Staging row ai*8 + ar holds angle 2 ar + ai of the chunk.
+__device__ __forceinline__ void k2_drain_real(const double *buf, double *out, const K2Desc &d, const size_t NN,
+                                              const int lane)
+{
+#pragma unroll 1
+    for (int hh = 0; hh < 2; ++hh) {
+        const int s = hh * 32 + lane;
+        if (s < d.s_lo || s >= d.s_hi) continue;
+        const double *src = buf + s;
+        double *dst = out + d.e00 + s;
+#pragma unroll
+        for (int ai = 0; ai < 2; ++ai) {
+            const int nrows = ai ? d.nrows1 : d.nrows0;
+            const double *sp = src + ai * 8 * K2_STG_LD;
+            double *dp = dst + (size_t)ai * NN;
+            if (nrows == 8) {                                         // all 8 loads in flight before the stores
+                double v[8];
+#pragma unroll
+                for (int ar = 0; ar < 8; ++ar) v[ar] = sp[ar * K2_STG_LD];
+#pragma unroll
+                for (int ar = 0; ar < 8; ++ar) dp[(size_t)(2 * ar) * NN] = v[ar];
+            } else {
+                for (int ar = 0; ar < nrows; ++ar) dp[(size_t)(2 * ar) * NN] = sp[ar * K2_STG_LD];
             }
         }
     }
 }
 
-// Epilogue of one mirror target: for each angle tile, stage the 8 x span tile (signs applied) and store it.
+// Epilogue of one mirror target: stage the 16 x span tile (signs applied), then hand it to the store warp
+// (real d) or drain it here with the fused phase (complex D).
 //   DESC = false: rows ascend with the quadrant row (targets (i,i') and (i,i'r));
 //   DESC = true : rows are the mirrored ones, written in ascending memory order ((ir,i'r) and (ir,i')).
 // val[ai][g][eo][h]: the butterfly-combined accumulators of this target.
@@ -183,10 +250,21 @@ __device__ __forceinline__ void k2_store_target(const K2Args &a, K2Ctx &cx, cons
 #pragma unroll
     for (int t = 0; t < 4; ++t) sb[t] = sigma_bit(DESC ? dib - t : dib + t);
     const size_t NN = (size_t)N * N;
-    // Stage the 16 x span tile (row ai*8 + r <-> angle 2r + ai of the chunk), then store whole column segments:
-    // 256 contiguous bytes per instruction for real d, 512 for complex D (fused phase).
+    const size_t e00 = (size_t)cx.b0 * NN + (size_t)col * N + row0;   // angle 0 of the chunk, staging position 0
     double *buf = cx.stg;
-    __syncwarp();
+    if (!CPLX) {
+        mbar_wait(cx.empty, (cx.tiles & 1) ^ 1);                     // the store warp has drained the previous tile
+        if (lane == 0) {
+            K2Desc d;
+            d.e00 = e00; d.s_lo = s_lo; d.s_hi = s_hi;
+            d.nrows0 = (int)max(0LL, min(8LL, (a.nb - cx.b0 + 1) / 2));
+            d.nrows1 = (int)max(0LL, min(8LL, (a.nb - cx.b0) / 2));
+            d.pad[0] = d.pad[1] = 0;
+            *cx.desc = d;
+        }
+    } else {
+        __syncwarp();
+    }
 #pragma unroll
     for (int ai = 0; ai < 2; ++ai) {
 #pragma unroll
@@ -202,52 +280,39 @@ __device__ __forceinline__ void k2_store_target(const K2Args &a, K2Ctx &cx, cons
         }
     }
     __syncwarp();
-    const size_t e00 = (size_t)cx.b0 * NN + (size_t)col * N + row0;   // angle 0 of the chunk, staging position 0
+    if (!CPLX) {
+        if (lane == 0) mbar_arrive(cx.full);                          // release: tile + descriptor are visible
+        ++cx.tiles;
+        return;
+    }
+    // complex D: exp(-i(m alpha + n gamma)) = (ca - i sa)(cg - i sg); m -> -m flips sa, n -> -n flips sg
 #pragma unroll 1
     for (int hh = 0; hh * 32 < span; ++hh) {
         const int s = hh * 32 + lane;
         if (s < s_lo || s >= s_hi) continue;
         const double *src = buf + s;
-        if (!CPLX) {
+        const int row = row0 + s;
+        const bool mneg = row < i0, nneg = col < i0;
+        const int qr = mneg ? (N - 1 - row - i0) : (row - i0);
+        const int qc = nneg ? (N - 1 - col - i0) : (col - i0);
 #pragma unroll
-            for (int ai = 0; ai < 2; ++ai) {
-                const long long bfirst = cx.b0 + ai;
-                if (bfirst >= a.nb) break;                            // warp-uniform
-                const int nrows = (int)min(8LL, (a.nb - bfirst + 1) / 2);
-                const double *sp = src + ai * 8 * K2_STG_LD;
-                double *dst = a.out + e00 + (size_t)ai * NN + s;
-#pragma unroll 4
-                for (int ar = 0; ar < nrows; ++ar) {                  // angle 2 ar + ai of the chunk
-                    *dst = *sp;
-                    sp += K2_STG_LD;
-                    dst += 2 * NN;
-                }
-            }
-        } else {
-            // exp(-i(m alpha + n gamma)) = (ca - i sa)(cg - i sg); m -> -m flips sa, n -> -n flips sg
-            const int row = row0 + s;
-            const bool mneg = row < i0, nneg = col < i0;
-            const int qr = mneg ? (N - 1 - row - i0) : (row - i0);
-            const int qc = nneg ? (N - 1 - col - i0) : (col - i0);
-#pragma unroll
-            for (int ai = 0; ai < 2; ++ai) {
-                const long long bfirst = cx.b0 + ai;
-                if (bfirst >= a.nb) break;                            // warp-uniform
-                const int nrows = (int)min(8LL, (a.nb - bfirst + 1) / 2);
-                const double *pa = cx.sPh + ai * Q + qr, *pg = cx.sPh + (2 * K2_ANG + ai) * Q + qc;
-                const double *sp = src + ai * 8 * K2_STG_LD;
-                double2 *dst = reinterpret_cast<double2 *>(a.out) + e00 + (size_t)ai * NN + s;
+        for (int ai = 0; ai < 2; ++ai) {
+            const long long bfirst = cx.b0 + ai;
+            if (bfirst >= a.nb) break;                                // warp-uniform
+            const int nrows = (int)min(8LL, (a.nb - bfirst + 1) / 2);
+            const double *pa = cx.sPh + ai * Q + qr, *pg = cx.sPh + (2 * K2_ANG + ai) * Q + qc;
+            const double *sp = src + ai * 8 * K2_STG_LD;
+            double2 *dst = reinterpret_cast<double2 *>(a.out) + e00 + (size_t)ai * NN + s;
 #pragma unroll 2
-                for (int ar = 0; ar < nrows; ++ar) {                  // angle 2 ar + ai of the chunk
-                    const double v = sp[ar * K2_STG_LD];
-                    const double ca = pa[(2 * ar) * Q], cg = pg[(2 * ar) * Q];
-                    double sa = pa[(K2_ANG + 2 * ar) * Q], sg = pg[(K2_ANG + 2 * ar) * Q];
-                    if (mneg) sa = -sa;
-                    if (nneg) sg = -sg;
-                    const double cr = ca * cg - sa * sg;
-                    const double ci = -(sa * cg + ca * sg);
-                    dst[(size_t)(2 * ar) * NN] = make_double2(v * cr, v * ci);
-                }
+            for (int ar = 0; ar < nrows; ++ar) {                      // angle 2 ar + ai of the chunk
+                const double v = sp[ar * K2_STG_LD];
+                const double ca = pa[(2 * ar) * Q], cg = pg[(2 * ar) * Q];
+                double sa = pa[(K2_ANG + 2 * ar) * Q], sg = pg[(K2_ANG + 2 * ar) * Q];
+                if (mneg) sa = -sa;
+                if (nneg) sg = -sg;
+                const double cr = ca * cg - sa * sg;
+                const double ci = -(sa * cg + ca * sg);
+                dst[(size_t)(2 * ar) * NN] = make_double2(v * cr, v * ci);
             }
         }
     }
@@ -300,10 +365,31 @@ __device__ __forceinline__ void k2_unit(const K2Args &a, K2Ctx &cx, const int qn
     }
 }
 
+// Store warp q (real-d kernels): drains the staged tiles of compute warp q until that warp has finished.
+__device__ __forceinline__ void k2_store_warp(const K2Args &a, double *sm, const K2Smem &L, const int q, const int lane)
+{
+    const size_t NN = (size_t)a.p.N * a.p.N;
+    void *full = sm + L.bars + q, *empty = sm + L.bars + K2_CWARPS + q;
+    const K2Desc *desc = reinterpret_cast<const K2Desc *>(sm + L.desc + q * (int)(sizeof(K2Desc) / 8));
+    const double *buf = sm + L.stg + q * (K2_STG_ROWS * K2_STG_LD);
+    unsigned phase = 0u;
+    for (;;) {
+        mbar_wait(full, phase);                                       // acquire: tile + descriptor are visible
+        const K2Desc d = *desc;
+        if (d.s_hi < 0) break;
+        k2_drain_real(buf, a.out, d, NN, lane);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty);                            // release: the buffer may be overwritten
+        phase ^= 1u;
+    }
+}
+
 template <bool HALF, bool CPLX>
-__global__ void __launch_bounds__(K2_THREADS, 1) k2_dmma_kernel(K2Args a)
+__global__ void __launch_bounds__(k2_threads(CPLX), 1) k2_dmma_kernel(K2Args a)
 {
     constexpr int GMAX = HALF ? 2 : 4;
+    constexpr int NT = k2_threads(CPLX);                   // all threads (setup phase)
+    constexpr int NC = K2_CWARPS * 32;                     // compute threads
     extern __shared__ __align__(16) double sm[];
     const PlanDev &p = a.p;
     const int Q = p.Q, Kp = p.Kp, ldu = p.ldu;
@@ -311,29 +397,46 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_dmma_kernel(K2Args a)
     const int ldt = L.ldt;
     double *sUQ = sm + L.uq, *sMu = sm + L.mu, *sW = sm + L.w, *sTc = sm + L.tc, *sTs = sm + L.ts;
     double *sPh = sm + L.ph;
-    int *sCounter = reinterpret_cast<int *>(sm + L.total);     // one int after the staging tiles
-    const int tid = threadIdx.x, warp = tid >> 5;
-    K2Ctx cx;
-    cx.sUQ = sUQ; cx.sTc = sTc; cx.sTs = sTs; cx.sPh = sPh;
-    cx.stg = sm + L.stg + warp * (K2_STG_ROWS * K2_STG_LD);
-    cx.ldu = ldu; cx.ldt = ldt; cx.N = p.N; cx.Q = Q; cx.i0 = p.N - Q; cx.zskip = p.zskip;
-    cx.Kp = Kp; cx.K0p = p.K0p; cx.twoj = p.twoj;
-    cx.lane = tid & 31; cx.r = cx.lane >> 2; cx.c = cx.lane & 3;
+    void *uq_bar = sm + L.bars + 2 * K2_CWARPS;
+    int *sCounter = reinterpret_cast<int *>(sm + L.bars + 2 * K2_CWARPS + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // one-time: UQ -> shared through the TMA engine (one bulk copy, mbarrier-signalled); zero pad rows, mu, w by hand
     {
-        void *mbar = reinterpret_cast<char *>(sm + L.total) + 8;   // 8 bytes after the unit counter
         const unsigned uq_bytes = (unsigned)(Q * ldu) * 8u;        // a multiple of 16: ldu is even
         if (tid == 0) {
-            mbar_init(mbar, 1);
-            mbar_expect_tx(mbar, uq_bytes);
-            bulk_load(sUQ, p.uq, uq_bytes, mbar);
+            mbar_init(uq_bar, 1);
+            for (int w = 0; w < 2 * K2_CWARPS; ++w) mbar_init(sm + L.bars + w, 1);
+            mbar_init_fence();
+            mbar_expect_tx(uq_bar, uq_bytes);
+            bulk_load(sUQ, p.uq, uq_bytes, uq_bar);
         }
-        for (int i = Q * ldu + tid; i < L.qpad * ldu; i += K2_THREADS) sUQ[i] = 0.0;
-        for (int i = tid; i < Kp; i += K2_THREADS) { sMu[i] = p.mu[i]; sW[i] = p.w[i]; }
-        __syncthreads();                                           // the mbarrier is initialised for everybody
-        mbar_wait(mbar, 0);
+        for (int i = Q * ldu + tid; i < L.qpad * ldu; i += NT) sUQ[i] = 0.0;
+        for (int i = tid; i < Kp; i += NT) { sMu[i] = p.mu[i]; sW[i] = p.w[i]; }
+        __syncthreads();                                           // the mbarriers are initialised for everybody
+        mbar_wait(uq_bar, 0);
     }
+
+    if (!CPLX) {
+        // warp specialisation: give the registers of the store warpgroup to the two compute warpgroups
+        if (warp >= K2_CWARPS) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(K2_REGS_STORE));
+            k2_store_warp(a, sm, L, warp - K2_CWARPS, lane);
+            return;
+        }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(K2_REGS_COMPUTE));
+    }
+
+    K2Ctx cx;
+    cx.sUQ = sUQ; cx.sTc = sTc; cx.sTs = sTs; cx.sPh = sPh;
+    cx.stg = sm + L.stg + warp * (K2_STG_ROWS * K2_STG_LD);
+    cx.desc = reinterpret_cast<K2Desc *>(sm + L.desc + warp * (int)(sizeof(K2Desc) / 8));
+    cx.full = sm + L.bars + warp; cx.empty = sm + L.bars + K2_CWARPS + warp;
+    cx.ldu = ldu; cx.ldt = ldt; cx.N = p.N; cx.Q = Q; cx.i0 = p.N - Q; cx.zskip = p.zskip;
+    cx.Kp = Kp; cx.K0p = p.K0p; cx.twoj = p.twoj;
+    cx.lane = lane; cx.r = lane >> 2; cx.c = lane & 3;
+    cx.tiles = 0;
+
     const int ngroups = L.qpad >> 4;
     const int upc = (ngroups + GMAX - 1) / GMAX;          // parts per column
     const int gbase = ngroups / upc, grem = ngroups - gbase * upc;   // the first grem parts have gbase+1 groups
@@ -343,10 +446,10 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_dmma_kernel(K2Args a)
     for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
         const long long b0 = ch * K2_ANG;
         cx.b0 = b0;
-        __syncthreads();                                   // previous chunk's readers are done (and UQ is in)
+        named_bar_sync(1, NC);                             // compute warps: previous chunk's table readers are done
         if (tid == 0) *sCounter = 0;
 #pragma unroll 1
-        for (int idx = tid; idx < K2_ANG * Kp; idx += K2_THREADS) {
+        for (int idx = tid; idx < K2_ANG * Kp; idx += NC) {
             const int ang = idx / Kp, kp = idx - ang * Kp;
             long long b = b0 + ang; if (b >= a.nb) b = a.nb - 1;
             double s, cs;
@@ -358,7 +461,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_dmma_kernel(K2Args a)
         }
         if (CPLX) {
 #pragma unroll 1
-            for (int idx = tid; idx < 2 * K2_ANG * Q; idx += K2_THREADS) {
+            for (int idx = tid; idx < 2 * K2_ANG * Q; idx += NC) {
                 const int which = idx / (K2_ANG * Q), rem = idx - which * (K2_ANG * Q);
                 const int ang = rem / Q, q = rem - ang * Q;
                 long long b = b0 + ang; if (b >= a.nb) b = a.nb - 1;
@@ -369,21 +472,34 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_dmma_kernel(K2Args a)
                 sPh[((2 * which + 1) * K2_ANG + ang) * Q + q] = s;
             }
         }
-        __syncthreads();
+        named_bar_sync(1, NC);
 
-        // dynamic unit scheduler (one shared counter per chunk): unit v -> part v / Q of column v % Q, so the
-        // larger parts of all columns are handed out before the smaller ones
+        // dynamic unit scheduler (one shared counter per chunk): unit v -> part v % upc of column v / upc.  The
+        // eight warps then work on adjacent columns, whose output is adjacent in memory: the 16 matrices of the
+        // chunk are written as (two) sequential streams each, which is what the L2/HBM write path needs -- the
+        // same bytes written as scattered 512-byte runs sustain only ~3.2 TB/s (tools/store_pattern_mb.cu)
 #pragma unroll 1
         for (;;) {
             int v = 0;
-            if (cx.lane == 0) v = atomicAdd(sCounter, 1);
+            if (lane == 0) v = atomicAdd(sCounter, 1);
             v = __shfl_sync(0xffffffffu, v, 0);
             if (v >= nunits) break;
-            const int part = v / Q, qn = v - part * Q;
+            const int qn = v / upc, part = v - qn * upc;           // column-major unit order: see the store-locality note
             const int g0 = part * gbase + min(part, grem);
             const int gcnt = gbase + (part < grem ? 1 : 0);
             k2_unit<HALF, CPLX>(a, cx, qn, g0, gcnt);
         }
+    }
+    if (!CPLX) {
+        // tell the store warp that this compute warp has finished
+        mbar_wait(cx.empty, (cx.tiles & 1) ^ 1);
+        if (lane == 0) {
+            K2Desc d;
+            d.e00 = 0; d.s_lo = 0; d.s_hi = -1; d.nrows0 = d.nrows1 = 0; d.pad[0] = d.pad[1] = 0;
+            *cx.desc = d;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(cx.full);
     }
 }
 
