@@ -193,6 +193,10 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
     a.p = pl.dev;
     a.alpha = alpha; a.beta = beta; a.gamma = gamma;
     a.nb = nb; a.out = out; a.equator = equator ? 1 : 0;
+    {
+        const char *e = getenv("WD_K2_HANDOFF");        // kernel-experiment knob
+        a.handoff = e ? atoi(e) : 1;
+    }
     size_t smem = 0;
     const bool fits = dmma_fits(h, pl.dev, cplx, &smem);
     int variant = h->variant;

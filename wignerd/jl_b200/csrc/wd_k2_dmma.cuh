@@ -86,11 +86,16 @@ __device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
 {
     while (!mbar_test(bar, parity)) { }
 }
-// named barrier (bar.sync is warp-aligned: the warp must be converged, hence the __syncwarp)
+// named barriers (bar.* is warp-aligned: the warp must be converged, hence the __syncwarp)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
     __syncwarp();
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads)
+{
+    __syncwarp();
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // what a store warp needs to know about a staged tile
@@ -133,6 +138,7 @@ struct K2Ctx {                  // per-thread constants of a compute warp
     int ldu, ldt, N, Q, i0, zskip, Kp, K0p, twoj;
     int lane, r, c;
     unsigned tiles;             // tiles handed to the store warp so far (mbarrier phase)
+    int bar_me, bar_other;      // named barriers of the midpoint hand-off between the two warps of a sub-partition (0 = off)
     long long b0;
 };
 
@@ -195,6 +201,7 @@ __device__ __forceinline__ void k2_mainloop(double (&acc)[2][2][GMAX][2][HALF ? 
             step(f1);
         }
         if (k < kend) step(f0);
+        if (cls == 0 && cx.bar_other) named_bar_arrive(cx.bar_other, 64);     // midpoint: release the partner warp
     }
 }
 
@@ -436,6 +443,14 @@ __global__ void __launch_bounds__(k2_threads(CPLX), 1) k2_dmma_kernel(K2Args a)
     cx.Kp = Kp; cx.K0p = p.K0p; cx.twoj = p.twoj;
     cx.lane = lane; cx.r = lane >> 2; cx.c = lane & 3;
     cx.tiles = 0;
+    // Anti-phase scheduling of the two compute warps (w, w+4) that share an SM sub-partition and hence one DMMA pipe:
+    // a warp may start a main loop only after its partner has passed the MIDPOINT of its own (one token, a pair of
+    // named barriers), so the main loops overlap pairwise by half and the epilogues of the pair never coincide.
+    // (Left alone the pair locks into phase: the warp that is alone in its main loop runs faster than half speed, so
+    // any offset shrinks, and then both are in their epilogues while the pipe idles.)  Measured: 11.4 -> 10.7 ms.
+    cx.bar_me = a.handoff ? 2 + warp : 0;
+    cx.bar_other = a.handoff ? 2 + (warp ^ 4) : 0;
+    if (a.handoff && (warp & 4)) named_bar_arrive(cx.bar_other, 64);       // warps 0..3 take the first turn
 
     const int ngroups = L.qpad >> 4;
     const int upc = (ngroups + GMAX - 1) / GMAX;          // parts per column
@@ -480,10 +495,11 @@ __global__ void __launch_bounds__(k2_threads(CPLX), 1) k2_dmma_kernel(K2Args a)
         // same bytes written as scattered 512-byte runs sustain only ~3.2 TB/s (tools/store_pattern_mb.cu)
 #pragma unroll 1
         for (;;) {
+            if (cx.bar_me) named_bar_sync(cx.bar_me, 64);
             int v = 0;
             if (lane == 0) v = atomicAdd(sCounter, 1);
             v = __shfl_sync(0xffffffffu, v, 0);
-            if (v >= nunits) break;
+            if (v >= nunits) { if (cx.bar_other) named_bar_arrive(cx.bar_other, 64); break; }
             const int qn = v / upc, part = v - qn * upc;           // column-major unit order: see the store-locality note
             const int g0 = part * gbase + min(part, grem);
             const int gcnt = gbase + (part < grem ? 1 : 0);

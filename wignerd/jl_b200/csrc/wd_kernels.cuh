@@ -138,6 +138,7 @@ struct K2Args {
     long long nb;
     double *out;                          // nb * N*N doubles (or * 2 for complex)
     int equator;                          // apply the exact zeros of :230-237 (plain kernel only)
+    int handoff;                          // DMMA kernel: midpoint hand-off between paired compute warps
 };
 
 template <bool CPLX>
