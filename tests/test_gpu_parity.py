@@ -118,6 +118,21 @@ def test_variants_agree(engine, twoj):
     assert np.abs(a - o.wignerd_batch(F(twoj, 2), betas)).max() < TOL
 
 
+@pytest.mark.parametrize("twoj,nb", [(241, 33), (300, 16), (401, 21), (512, 50)])
+def test_streaming_kernel_vs_plain_and_oracle(engine, twoj, nb):
+    """tables that do not fit in shared memory take the mu-streaming DMMA kernel (auto variant); the plain
+    FP64-ALU kernel (variant 1) is the independent cross-check"""
+    betas = np.random.default_rng(twoj).uniform(-1.0, 4.0, nb)
+    try:
+        engine.set_variant(1)
+        a = engine.wignerd_batch(F(twoj, 2), betas).copy()
+    finally:
+        engine.set_variant(0)
+    b = engine.wignerd_batch(F(twoj, 2), betas)
+    assert np.abs(a - b).max() < 1e-13
+    assert np.abs(b - o.wignerd_batch(F(twoj, 2), betas)).max() < TOL
+
+
 @pytest.mark.parametrize("twoj", [300, 600, 1024])
 def test_large_j_vs_oracle(engine, twoj):
     betas = np.array([0.0, 0.4, pi / 2, 2.9, pi])

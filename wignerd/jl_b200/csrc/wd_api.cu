@@ -6,6 +6,7 @@
 #include "../../../include/wignerd_b200.h"
 #include "wd_kernels.cuh"
 #include "wd_k2_dmma.cuh"
+#include "wd_k2_stream.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -65,6 +66,7 @@ struct wd_handle_s {
     bool table_dirty = true;
     int *d_flag = nullptr;           // error flag / scratch ints
     bool attr_set[2][2] = {{false, false}, {false, false}};
+    bool attr_set_stream[2] = {false, false};
 };
 
 namespace {
@@ -184,6 +186,40 @@ int launch_dmma(wd_handle_t h, const K2Args &a, size_t smem)
     return WD_OK;
 }
 
+// Streaming DMMA kernel (real d, table too large for shared memory): trig table pass + contraction.
+template <bool HALF>
+int launch_stream(wd_handle_t h, const K2Args &a)
+{
+    const K2SSmem L = k2s_smem_layout(HALF);
+    const size_t smem = (size_t)L.total * sizeof(double);
+    if (!h->attr_set_stream[HALF]) {
+        CU(cudaFuncSetAttribute(k2_stream_kernel<HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+        h->attr_set_stream[HALF] = true;
+    }
+    K2SArgs sa;
+    sa.base = a;
+    sa.nck0 = k2s_nchunks(a.p.K0p);
+    sa.nck1 = k2s_nchunks(a.p.K1p);
+    const long long nac = (a.nb + K2_ANG - 1) / K2_ANG;
+    const size_t ntrig = (size_t)nac * (sa.nck0 + sa.nck1) * K2S_TRIG_TILE;
+    double *trig = nullptr;
+    CU(cudaMallocAsync(&trig, ntrig * sizeof(double), h->stream));
+    sa.trig = trig;
+    const long long work = nac * (sa.nck0 + sa.nck1) * K2_ANG * K2S_KC;
+    const int tblocks = (int)std::min<long long>((work + 255) / 256, (long long)h->num_sms * 16);
+    k2s_trig_kernel<<<tblocks, 256, 0, h->stream>>>(a.p, a.beta, a.nb, trig, sa.nck0, sa.nck1);
+    const int gmax = HALF ? 2 : 4;
+    const int ngroups = (a.p.Q + 15) / 16;
+    const long long ntiles = nac * ((ngroups + gmax - 1) / gmax) * ((a.p.Q + K2_CWARPS - 1) / K2_CWARPS);
+    const int grid = (int)std::min<long long>(ntiles, h->num_sms);
+    k2_stream_kernel<HALF><<<grid, k2_threads(false), smem, h->stream>>>(sa);
+    h->launches += 2;
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(trig, h->stream);
+    if (e != cudaSuccess) return fail(WD_ERR_CUDA, "streaming kernel launch failed: %s", cudaGetErrorString(e));
+    return WD_OK;
+}
+
 // d (or D) for nb generic angles, all pointers on the device.
 int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const double *beta, const double *gamma,
                     long long nb, double *out, bool cplx, bool equator)
@@ -208,6 +244,8 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
         if (half) return cplx ? launch_dmma<true, true>(h, a, smem) : launch_dmma<true, false>(h, a, smem);
         return cplx ? launch_dmma<false, true>(h, a, smem) : launch_dmma<false, false>(h, a, smem);
     }
+    // real d for a table that does not fit in shared memory: the streaming DMMA kernel
+    if (!cplx && !equator && variant != 1) return half ? launch_stream<true>(h, a) : launch_stream<false>(h, a);
     const size_t psm = 2 * (size_t)pl.dev.Kp * sizeof(double);
     const int Q = pl.dev.Q;
     const int gy = std::max(1, std::min(64, (Q * Q + 255) / 256));

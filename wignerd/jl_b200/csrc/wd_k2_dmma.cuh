@@ -373,12 +373,10 @@ __device__ __forceinline__ void k2_unit(const K2Args &a, K2Ctx &cx, const int qn
 }
 
 // Store warp q (real-d kernels): drains the staged tiles of compute warp q until that warp has finished.
-__device__ __forceinline__ void k2_store_warp(const K2Args &a, double *sm, const K2Smem &L, const int q, const int lane)
+__device__ __forceinline__ void k2_store_warp(const K2Args &a, const double *buf, const K2Desc *desc, void *full,
+                                              void *empty, const int lane)
 {
     const size_t NN = (size_t)a.p.N * a.p.N;
-    void *full = sm + L.bars + q, *empty = sm + L.bars + K2_CWARPS + q;
-    const K2Desc *desc = reinterpret_cast<const K2Desc *>(sm + L.desc + q * (int)(sizeof(K2Desc) / 8));
-    const double *buf = sm + L.stg + q * (K2_STG_ROWS * K2_STG_LD);
     unsigned phase = 0u;
     for (;;) {
         mbar_wait(full, phase);                                       // acquire: tile + descriptor are visible
@@ -428,7 +426,10 @@ __global__ void __launch_bounds__(k2_threads(CPLX), 1) k2_dmma_kernel(K2Args a)
         // warp specialisation: give the registers of the store warpgroup to the two compute warpgroups
         if (warp >= K2_CWARPS) {
             asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(K2_REGS_STORE));
-            k2_store_warp(a, sm, L, warp - K2_CWARPS, lane);
+            const int q = warp - K2_CWARPS;
+            k2_store_warp(a, sm + L.stg + q * (K2_STG_ROWS * K2_STG_LD),
+                          reinterpret_cast<const K2Desc *>(sm + L.desc + q * (int)(sizeof(K2Desc) / 8)), sm + L.bars + q,
+                          sm + L.bars + K2_CWARPS + q, lane);
             return;
         }
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(K2_REGS_COMPUTE));

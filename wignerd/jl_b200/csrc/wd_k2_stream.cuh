@@ -1,0 +1,277 @@
+// wd_k2_stream.cuh -- the DMMA contraction for j whose eigenvector table does not fit in shared memory
+// (2j > ~240, up to the supported maximum): same mathematics, warp unit, epilogue and store warps as
+// k2_dmma_kernel (wd_k2_dmma.cuh), but the mu axis is streamed.
+//
+//   CTA tile = 16 angles x one block of 16*GMAX quadrant rows x 8 quadrant columns (one column per compute warp).
+//   The mu axis is cut into chunks of <= 32 columns per eigenvector class; per chunk a stage of a 3-deep ring in
+//   shared memory receives (cp.async, 16-byte granules -> SASS LDGSTS)
+//       - the row block of UQ      [16*GMAX rows][32 (+2 pad)]
+//       - the 8 column rows of UQ  [8][32 (+2 pad)]
+//       - the trig tile            [cos|sin][16 angles][32 (+4 pad)]   from a table precomputed once per call
+//         (k2s_trig_kernel) -- in-kernel trig would be recomputed by every one of the ~Q^2/512 tiles of a chunk.
+//   One named barrier per chunk; accumulators live in registers across the whole mu loop.
+//   Shared-memory traffic per DMMA equals the resident kernel's; global->shared traffic is ~10 B/clk/SM.
+#pragma once
+#include "wd_k2_dmma.cuh"
+
+namespace wd {
+
+constexpr int K2S_KC = 32;                 // mu columns per chunk
+constexpr int K2S_LDU = K2S_KC + 2;        // == 2 mod 4: conflict-free stride-2 row fragments
+constexpr int K2S_LDT = K2S_KC + 4;        // == 4 mod 8: conflict-free 8-row fragments
+constexpr int K2S_STAGES = 3;
+constexpr int K2S_TRIG_TILE = 2 * K2_ANG * K2S_LDT;       // doubles per (angle chunk, mu chunk) trig tile
+
+__host__ __device__ inline int k2s_nchunks(int Kxp) { return (Kxp + K2S_KC - 1) / K2S_KC; }
+
+struct K2SArgs {
+    K2Args base;
+    const double *trig;        // [angle chunk][mu chunk][2][16][K2S_LDT]
+    int nck0, nck1;            // mu chunks of class 0 / class 1
+};
+
+struct K2SSmem {               // offsets in doubles
+    int stage, stage_size, uqr, uqc, trig, stg, desc, bars, total;
+    int rows;                  // 16 * GMAX
+};
+__host__ __device__ inline K2SSmem k2s_smem_layout(bool half)
+{
+    K2SSmem s;
+    s.rows = 16 * (half ? 2 : 4);
+    s.uqr = 0;
+    s.uqc = s.rows * K2S_LDU;
+    s.trig = s.uqc + K2_CWARPS * K2S_LDU;
+    s.stage_size = s.trig + K2S_TRIG_TILE;
+    s.stage_size = (s.stage_size + 1) & ~1;
+    int o = 0;
+    s.stage = o; o += K2S_STAGES * s.stage_size;
+    s.stg = o;   o += K2_CWARPS * K2_STG_ROWS * K2_STG_LD;
+    s.desc = o;  o += K2_CWARPS * (int)(sizeof(K2Desc) / 8);
+    s.bars = o;  o += 2 * K2_CWARPS + 2;
+    s.total = o;
+    return s;
+}
+
+// trig table: T[ac][kc][0|1][row(angle)][col] = w * cos|sin(mu * beta), zero on the pads
+__global__ void __launch_bounds__(256) k2s_trig_kernel(PlanDev p, const double *__restrict__ beta, long long nb,
+                                                       double *__restrict__ trig, int nck0, int nck1)
+{
+    const int nck = nck0 + nck1;
+    const long long nac = (nb + K2_ANG - 1) / K2_ANG;
+    const long long total = nac * nck * K2_ANG * K2S_KC;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int col = (int)(i % K2S_KC);
+        const int ang = (int)((i / K2S_KC) % K2_ANG);
+        const int kc = (int)((i / (K2S_KC * K2_ANG)) % nck);
+        const long long ac = i / ((long long)K2S_KC * K2_ANG * nck);
+        const int cls = kc >= nck0;
+        const int kbase = cls ? p.K0p + (kc - nck0) * K2S_KC : kc * K2S_KC;
+        const int kend = cls ? p.Kp : p.K0p;
+        const int kp = kbase + col;
+        long long b = ac * K2_ANG + ang; if (b >= nb) b = nb - 1;
+        double c = 0.0, s = 0.0;
+        if (kp < kend) {
+            sincos(p.mu[kp] * beta[b], &s, &c);            // fl(mu*beta) then sincos, like src/WignerD.jl:199
+            const double w = p.w[kp];
+            c *= w; s *= w;
+        }
+        double *tile = trig + ((size_t)ac * nck + kc) * K2S_TRIG_TILE;
+        const int row = k2_trig_row(ang);
+        tile[row * K2S_LDT + col] = c;
+        tile[(K2_ANG + row) * K2S_LDT + col] = s;
+    }
+}
+
+__device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// DMMAs of one mu chunk for one class: the two-fragment-set pipeline of k2_mainloop over nsteps k-steps.
+template <bool HALF, int GMAX>
+__device__ __forceinline__ void k2s_chunk(double (&acc)[2][GMAX][2][HALF ? 2 : 1][2], const double *tA, const double *tB,
+                                          const double *un, const double *ub, const int nsteps)
+{
+    constexpr int gs = 16 * K2S_LDU, t8 = 8 * K2S_LDT, ldu = K2S_LDU;
+    struct Frag { double un, ta[2], tb[2], be[GMAX], bo[GMAX]; };
+    auto load = [&](Frag &f, const int k) {
+        f.un = un[k];
+#pragma unroll
+        for (int ai = 0; ai < 2; ++ai) { f.ta[ai] = tA[ai * t8 + k]; f.tb[ai] = tB[ai * t8 + k]; }
+#pragma unroll
+        for (int g = 0; g < GMAX; ++g) { f.be[g] = ub[g * gs + k]; f.bo[g] = ub[g * gs + ldu + k]; }
+    };
+    auto step = [&](Frag &f) {
+#pragma unroll
+        for (int ai = 0; ai < 2; ++ai) { f.ta[ai] *= f.un; f.tb[ai] *= f.un; }
+#pragma unroll
+        for (int g = 0; g < GMAX; ++g) {
+#pragma unroll
+            for (int ai = 0; ai < 2; ++ai) {
+                dmma(acc[ai][g][0][0], f.ta[ai], f.be[g]);
+                dmma(acc[ai][g][1][0], f.tb[ai], f.bo[g]);
+                if (HALF) {
+                    dmma(acc[ai][g][0][1], f.tb[ai], f.be[g]);
+                    dmma(acc[ai][g][1][1], f.ta[ai], f.bo[g]);
+                }
+            }
+        }
+    };
+    // the stage rows are K2S_KC wide and followed by pad columns inside the stage, so the look-ahead load of the
+    // step after the last one stays inside the stage
+    Frag f0, f1;
+    load(f0, 0);
+    int k = 0;
+    const int kend = 4 * nsteps;
+#pragma unroll 1
+    for (; k + 4 < kend; k += 8) {
+        load(f1, k + 4);
+        step(f0);
+        load(f0, (k + 8 < K2S_KC) ? k + 8 : 0);
+        step(f1);
+    }
+    if (k < kend) step(f0);
+}
+
+template <bool HALF>
+__global__ void __launch_bounds__(k2_threads(false), 1) k2_stream_kernel(K2SArgs sa)
+{
+    constexpr int GMAX = HALF ? 2 : 4;
+    constexpr int NALT = HALF ? 2 : 1;
+    constexpr int NC = K2_CWARPS * 32;
+    constexpr int ROWS = 16 * GMAX;
+    extern __shared__ __align__(16) double sm[];
+    const K2Args &a = sa.base;
+    const PlanDev &p = a.p;
+    const int Q = p.Q, ldu = p.ldu;
+    const K2SSmem L = k2s_smem_layout(HALF);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int w = 0; w < 2 * K2_CWARPS; ++w) mbar_init(sm + L.bars + w, 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+    if (warp >= K2_CWARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(K2_REGS_STORE));
+        const int q = warp - K2_CWARPS;
+        k2_store_warp(a, sm + L.stg + q * (K2_STG_ROWS * K2_STG_LD),
+                      reinterpret_cast<const K2Desc *>(sm + L.desc + q * (int)(sizeof(K2Desc) / 8)), sm + L.bars + q,
+                      sm + L.bars + K2_CWARPS + q, lane);
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(K2_REGS_COMPUTE));
+
+    K2Ctx cx;
+    cx.sUQ = nullptr; cx.sTc = nullptr; cx.sTs = nullptr; cx.sPh = nullptr;
+    cx.stg = sm + L.stg + warp * (K2_STG_ROWS * K2_STG_LD);
+    cx.desc = reinterpret_cast<K2Desc *>(sm + L.desc + warp * (int)(sizeof(K2Desc) / 8));
+    cx.full = sm + L.bars + warp; cx.empty = sm + L.bars + K2_CWARPS + warp;
+    cx.ldu = ldu; cx.ldt = 0; cx.N = p.N; cx.Q = Q; cx.i0 = p.N - Q; cx.zskip = p.zskip;
+    cx.Kp = p.Kp; cx.K0p = p.K0p; cx.twoj = p.twoj;
+    cx.lane = lane; cx.r = lane >> 2; cx.c = lane & 3;
+    cx.tiles = 0; cx.bar_me = 0; cx.bar_other = 0;
+    const int r = cx.r, c = cx.c;
+
+    const int ngroups = (Q + 15) >> 4;
+    const int nrb = (ngroups + GMAX - 1) / GMAX;           // row blocks
+    const int ncb = (Q + K2_CWARPS - 1) / K2_CWARPS;       // column blocks (8 columns each)
+    const long long nac = (a.nb + K2_ANG - 1) / K2_ANG;
+    const long long ntiles = nac * nrb * ncb;
+    const int nck0 = sa.nck0, nck = sa.nck0 + sa.nck1;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int cb = (int)(tile % ncb);
+        const int rb = (int)((tile / ncb) % nrb);
+        const long long ac = tile / ((long long)ncb * nrb);
+        cx.b0 = ac * K2_ANG;
+        const int g0 = rb * GMAX, gcnt = min(GMAX, ngroups - g0);
+        const int qn = cb * K2_CWARPS + warp;
+        const bool active = qn < Q;
+        const int pe = qn & 1;
+
+        // issue the cp.async copies of mu chunk kc into its ring stage (all compute threads take part)
+        auto issue = [&](const int kc) {
+            double *st = sm + L.stage + (kc % K2S_STAGES) * L.stage_size;
+            const int cls = kc >= nck0;
+            const int kbase = cls ? p.K0p + (kc - nck0) * K2S_KC : kc * K2S_KC;
+            const int kend = cls ? p.Kp : p.K0p;
+            const int gran = min(K2S_KC, kend - kbase) >> 1;            // 16-byte granules per row (widths are multiples of 4)
+            // UQ rows: ROWS of the row block, then the 8 column rows (row indices clamped: values past Q are never stored)
+            for (int i = tid; i < (ROWS + K2_CWARPS) * (K2S_KC / 2); i += NC) {
+                const int row = i / (K2S_KC / 2), g = i - row * (K2S_KC / 2);
+                if (g >= gran) continue;
+                const int q = row < ROWS ? min(16 * g0 + row, Q - 1) : min(cb * K2_CWARPS + (row - ROWS), Q - 1);
+                cp_async16(st + row * K2S_LDU + 2 * g, p.uq + (size_t)q * ldu + kbase + 2 * g);
+            }
+            const double *tsrc = sa.trig + ((size_t)ac * nck + kc) * K2S_TRIG_TILE;
+            for (int i = tid; i < K2S_TRIG_TILE / 2; i += NC) cp_async16(st + L.trig + 2 * i, tsrc + 2 * i);
+            cp_async_commit();
+        };
+
+        double acc[2][2][GMAX][2][NALT][2];
+#pragma unroll
+        for (int i = 0; i < 2 * 2 * GMAX * 2 * NALT * 2; ++i) (&acc[0][0][0][0][0][0])[i] = 0.0;
+
+        named_bar_sync(1, NC);                              // everybody is done with the previous tile's stages
+        issue(0);
+        if (nck > 1) issue(1); else cp_async_commit();
+#pragma unroll 1
+        for (int kc = 0; kc < nck; ++kc) {
+            cp_async_wait<1>();                             // this thread's copies of chunk kc have landed ...
+            named_bar_sync(1, NC);                          // ... and everybody else's; chunk kc-1 is consumed by all
+            if (kc + 2 < nck) issue(kc + 2); else cp_async_commit();
+            if (active) {
+                const double *st = sm + L.stage + (kc % K2S_STAGES) * L.stage_size;
+                const int cls = kc >= nck0;
+                const int kbase = cls ? p.K0p + (kc - nck0) * K2S_KC : kc * K2S_KC;
+                const int kend = cls ? p.Kp : p.K0p;
+                const int nsteps = min(K2S_KC, kend - kbase) >> 2;
+                const double *tc = st + L.trig + r * K2S_LDT + c, *ts = tc + K2_ANG * K2S_LDT;
+                const double *tA = pe ? ts : tc, *tB = pe ? tc : ts;
+                const double *un = st + L.uqc + warp * K2S_LDU + c;
+                const double *ub = st + L.uqr + (2 * r) * K2S_LDU + c;
+                if (cls == 0) k2s_chunk<HALF, GMAX>(acc[0], tA, tB, un, ub, nsteps);
+                else k2s_chunk<HALF, GMAX>(acc[1], tA, tB, un, ub, nsteps);
+            }
+        }
+        if (!active) continue;
+
+        // ---- epilogue: identical to the resident kernel ------------------------------------------------------
+        double vs[2][GMAX][2][2], vd[2][GMAX][2][2];
+#pragma unroll
+        for (int ai = 0; ai < 2; ++ai)
+#pragma unroll
+            for (int g = 0; g < GMAX; ++g)
+#pragma unroll
+                for (int eo = 0; eo < 2; ++eo)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        vs[ai][g][eo][h] = acc[0][ai][g][eo][0][h] + acc[1][ai][g][eo][0][h];
+                        vd[ai][g][eo][h] = acc[0][ai][g][eo][NALT - 1][h] - acc[1][ai][g][eo][NALT - 1][h];
+                    }
+        const int ip = cx.i0 + qn, ipr = cx.N - 1 - ip;
+        const int qbase = 16 * g0;
+        k2_store_target<false, false, GMAX>(a, cx, vs, ip, qbase, gcnt);
+        k2_store_target<false, true, GMAX>(a, cx, vd, ip, qbase, gcnt);
+        if (qn >= cx.zskip) {
+            k2_store_target<false, true, GMAX>(a, cx, vs, ipr, qbase, gcnt);
+            k2_store_target<false, false, GMAX>(a, cx, vd, ipr, qbase, gcnt);
+        }
+    }
+    cp_async_wait<0>();
+    // tell the store warp that this compute warp has finished
+    mbar_wait(cx.empty, (cx.tiles & 1) ^ 1);
+    if (lane == 0) {
+        K2Desc d;
+        d.e00 = 0; d.s_lo = 0; d.s_hi = -1; d.nrows0 = d.nrows1 = 0; d.pad[0] = d.pad[1] = 0;
+        *cx.desc = d;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(cx.full);
+}
+
+}  // namespace wd
