@@ -67,6 +67,10 @@ struct wd_handle_s {
     int *d_flag = nullptr;           // error flag / scratch ints
     bool attr_set[2][2] = {{false, false}, {false, false}};
     bool attr_set_stream[2] = {false, false};
+    // host-path workspace, kept across calls (grow-only): angle vectors and two output slabs + their events
+    double *ws_ang = nullptr, *ws_slab[2] = {nullptr, nullptr};
+    size_t ws_ang_bytes = 0, ws_slab_bytes[2] = {0, 0};
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -163,11 +167,15 @@ int get_plan(wd_handle_t h, int twoj, const Plan **out)
     return WD_OK;
 }
 
-bool dmma_fits(wd_handle_t h, const PlanDev &p, bool cplx, size_t *bytes)
+bool dmma_fits(wd_handle_t h, const PlanDev &p, bool cplx, size_t *bytes, int *nsub, int nsub_max)
 {
-    const K2Smem L = k2_smem_layout(p.Q, p.Kp, p.ldu, cplx);
-    *bytes = (size_t)L.total * sizeof(double);
-    return *bytes <= h->smem_optin;
+    for (int ns = cplx ? 1 : nsub_max; ns >= 1; --ns) {
+        const K2Smem L = k2_smem_layout(p.Q, p.Kp, p.ldu, cplx, ns);
+        *bytes = (size_t)L.total * sizeof(double);
+        *nsub = ns;
+        if (*bytes <= h->smem_optin) return true;
+    }
+    return false;
 }
 
 template <bool HALF, bool CPLX>
@@ -178,7 +186,7 @@ int launch_dmma(wd_handle_t h, const K2Args &a, size_t smem)
                                 (int)h->smem_optin));
         h->attr_set[HALF][CPLX] = true;
     }
-    const long long nchunks = (a.nb + K2_ANG - 1) / K2_ANG;
+    const long long nchunks = (a.nb + K2_ANG * a.nsub - 1) / (K2_ANG * a.nsub);
     const int grid = (int)std::min<long long>(nchunks, h->num_sms);
     k2_dmma_kernel<HALF, CPLX><<<grid, k2_threads(CPLX), smem, h->stream>>>(a);
     h->launches++;
@@ -234,10 +242,19 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
         a.handoff = e ? atoi(e) : 1;
     }
     size_t smem = 0;
-    const bool fits = dmma_fits(h, pl.dev, cplx, &smem);
+    // two 16-angle chunks per barrier phase measured no gain (10.98 vs 11.25 ms at cfg-2): one chunk unless asked for
+    int nsub_max = 1;
+    {
+        const char *e = getenv("WD_K2_NSUB");            // kernel-experiment knob
+        if (e && atoi(e) == 2) nsub_max = 2;
+    }
+    int nsub = 1;
+    const bool fits = dmma_fits(h, pl.dev, cplx, &smem, &nsub, nsub_max);
+    a.nsub = nsub;
     int variant = h->variant;
     if (variant == 2 && !fits) return fail(WD_ERR_UNSUPPORTED, "2j = %d does not fit the DMMA kernel (%zu B of shared memory)", pl.dev.twoj, smem);
     // Equator() requests (single matrices, exact zeros of :230-237) take the plain kernel
+    if (variant == 3 && !cplx && !equator) return (pl.dev.twoj & 1) ? launch_stream<true>(h, a) : launch_stream<false>(h, a);
     const bool use_dmma = !equator && ((variant == 2) || (variant == 0 && fits));
     const bool half = pl.dev.twoj & 1;
     if (use_dmma) {
@@ -272,8 +289,17 @@ int contract_host(wd_handle_t h, const Plan &pl, const double *alpha, const doub
     CU(cudaSetDevice(h->device));
     const size_t per = (size_t)pl.dev.N * pl.dev.N * (cplx ? 2 : 1);          // doubles per matrix
     const int nang = cplx ? 3 : 1;
-    double *d_ang = nullptr;
-    CU(cudaMalloc(&d_ang, (size_t)nb * nang * sizeof(double)));
+    auto grow = [](double **buf, size_t *have, size_t need) -> cudaError_t {
+        if (*have >= need) return cudaSuccess;
+        if (*buf) cudaFree(*buf);
+        *buf = nullptr; *have = 0;
+        cudaError_t e = cudaMalloc(buf, need);
+        if (e == cudaSuccess) *have = need;
+        return e;
+    };
+    if (grow(&h->ws_ang, &h->ws_ang_bytes, (size_t)nb * nang * sizeof(double)) != cudaSuccess)
+        return fail(WD_ERR_NOMEM, "cudaMalloc of the angle workspace failed");
+    double *d_ang = h->ws_ang;
     cudaMemcpyAsync(d_ang, beta, nb * sizeof(double), cudaMemcpyHostToDevice, h->stream);
     if (cplx) {
         cudaMemcpyAsync(d_ang + nb, alpha, nb * sizeof(double), cudaMemcpyHostToDevice, h->stream);
@@ -284,36 +310,30 @@ int contract_host(wd_handle_t h, const Plan &pl, const double *alpha, const doub
     slab = std::min(slab, nb);
     if (slab > K2_ANG) slab -= slab % K2_ANG;
     const int nbuf = (slab < nb) ? 2 : 1;
-    double *d_out[2] = {nullptr, nullptr};
-    cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
     int rc = WD_OK;
     for (int i = 0; i < nbuf && rc == WD_OK; ++i) {
-        if (cudaMalloc(&d_out[i], (size_t)slab * per * sizeof(double)) != cudaSuccess)
+        if (grow(&h->ws_slab[i], &h->ws_slab_bytes[i], (size_t)slab * per * sizeof(double)) != cudaSuccess)
             rc = fail(WD_ERR_NOMEM, "cudaMalloc of a %zu-byte output slab failed", (size_t)slab * per * sizeof(double));
-        cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
+        if (!h->ev_done[i]) {
+            cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming);
+        }
     }
     int k = 0;
     for (long long b0 = 0; b0 < nb && rc == WD_OK; b0 += slab, ++k) {
         const int i = k % nbuf;
         const long long cnt = std::min(slab, nb - b0);
-        if (k >= nbuf) cudaStreamWaitEvent(h->stream, copied[i], 0);        // slab buffer free again
+        if (k >= nbuf) cudaStreamWaitEvent(h->stream, h->ev_copied[i], 0);  // slab buffer free again
         rc = contract_device(h, pl, cplx ? d_ang + nb + b0 : nullptr, d_ang + b0, cplx ? d_ang + 2 * nb + b0 : nullptr,
-                             cnt, d_out[i], cplx, equator);
+                             cnt, h->ws_slab[i], cplx, equator);
         if (rc) break;
-        cudaEventRecord(done[i], h->stream);
-        cudaStreamWaitEvent(h->copy_stream, done[i], 0);
-        cudaMemcpyAsync(out + (size_t)b0 * per, d_out[i], (size_t)cnt * per * sizeof(double), cudaMemcpyDeviceToHost,
+        cudaEventRecord(h->ev_done[i], h->stream);
+        cudaStreamWaitEvent(h->copy_stream, h->ev_done[i], 0);
+        cudaMemcpyAsync(out + (size_t)b0 * per, h->ws_slab[i], (size_t)cnt * per * sizeof(double), cudaMemcpyDeviceToHost,
                         h->copy_stream);
-        cudaEventRecord(copied[i], h->copy_stream);
+        cudaEventRecord(h->ev_copied[i], h->copy_stream);
     }
     cudaError_t e1 = cudaStreamSynchronize(h->stream), e2 = cudaStreamSynchronize(h->copy_stream);
-    for (int i = 0; i < nbuf; ++i) {
-        if (d_out[i]) cudaFree(d_out[i]);
-        if (done[i]) cudaEventDestroy(done[i]);
-        if (copied[i]) cudaEventDestroy(copied[i]);
-    }
-    cudaFree(d_ang);
     if (rc) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess)
         return fail(WD_ERR_CUDA, "contraction failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
@@ -494,6 +514,12 @@ int wd_destroy(wd_handle_t h)
     for (auto &kv : h->plans) cudaFree(kv.second.uq);
     if (h->d_table) cudaFree(h->d_table);
     if (h->d_flag) cudaFree(h->d_flag);
+    if (h->ws_ang) cudaFree(h->ws_ang);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ws_slab[i]) cudaFree(h->ws_slab[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+        if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    }
     cudaStreamDestroy(h->own_stream);
     cudaStreamDestroy(h->copy_stream);
     delete h;
@@ -534,7 +560,7 @@ int wd_cache_clear(wd_handle_t h)
 int wd_set_variant(wd_handle_t h, int variant)
 {
     if (!h) return fail(WD_ERR_ASSERT, "null handle");
-    if (variant < 0 || variant > 2) return fail(WD_ERR_ASSERT, "variant must be 0, 1 or 2");
+    if (variant < 0 || variant > 3) return fail(WD_ERR_ASSERT, "variant must be 0..3");
     h->variant = variant;
     return WD_OK;
 }

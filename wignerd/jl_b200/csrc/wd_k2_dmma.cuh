@@ -110,7 +110,7 @@ struct K2Smem {                 // offsets in doubles, computed identically on h
     int uq, mu, w, tc, ts, ph, stg, desc, bars, total;
     int ldt, qpad;
 };
-__host__ __device__ inline K2Smem k2_smem_layout(int Q, int Kp, int ldu, bool cplx)
+__host__ __device__ inline K2Smem k2_smem_layout(int Q, int Kp, int ldu, bool cplx, int nsub = 1)
 {
     K2Smem s;
     s.ldt = Kp | 4;                        // == 4 mod 8: conflict-free for 8 consecutive rows x 4 cols
@@ -119,8 +119,8 @@ __host__ __device__ inline K2Smem k2_smem_layout(int Q, int Kp, int ldu, bool cp
     s.uq = o;  o += s.qpad * ldu;
     s.mu = o;  o += Kp;
     s.w = o;   o += Kp;
-    s.tc = o;  o += K2_ANG * s.ldt;
-    s.ts = o;  o += K2_ANG * s.ldt;
+    s.tc = o;  o += nsub * K2_ANG * s.ldt;             // nsub chunks of 16 angles share one barrier phase
+    s.ts = o;  o += nsub * K2_ANG * s.ldt;
     s.ph = o;  o += cplx ? 4 * K2_ANG * Q : 0;          // cos(m a), sin(m a), cos(n g), sin(n g)  [16][Q]
     o = (o + 1) & ~1;
     s.stg = o;  o += K2_CWARPS * K2_STG_ROWS * K2_STG_LD;
@@ -398,7 +398,8 @@ __global__ void __launch_bounds__(k2_threads(CPLX), 1) k2_dmma_kernel(K2Args a)
     extern __shared__ __align__(16) double sm[];
     const PlanDev &p = a.p;
     const int Q = p.Q, Kp = p.Kp, ldu = p.ldu;
-    const K2Smem L = k2_smem_layout(Q, Kp, ldu, CPLX);
+    const int nsub = CPLX ? 1 : a.nsub;                    // 16-angle chunks per barrier phase ("super-chunk")
+    const K2Smem L = k2_smem_layout(Q, Kp, ldu, CPLX, nsub);
     const int ldt = L.ldt;
     double *sUQ = sm + L.uq, *sMu = sm + L.mu, *sW = sm + L.w, *sTc = sm + L.tc, *sTs = sm + L.ts;
     double *sPh = sm + L.ph;
@@ -457,21 +458,23 @@ __global__ void __launch_bounds__(k2_threads(CPLX), 1) k2_dmma_kernel(K2Args a)
     const int upc = (ngroups + GMAX - 1) / GMAX;          // parts per column
     const int gbase = ngroups / upc, grem = ngroups - gbase * upc;   // the first grem parts have gbase+1 groups
     const int nunits = Q * upc;
-    const long long nchunks = (a.nb + K2_ANG - 1) / K2_ANG;
+    const int sang = K2_ANG * nsub;                        // angles per barrier phase
+    const long long nchunks = (a.nb + sang - 1) / sang;
 
     for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-        const long long b0 = ch * K2_ANG;
+        const long long b0 = ch * sang;
+        const int nsub_here = (int)min((long long)nsub, (a.nb - b0 + K2_ANG - 1) / K2_ANG);
         cx.b0 = b0;
         named_bar_sync(1, NC);                             // compute warps: previous chunk's table readers are done
         if (tid == 0) *sCounter = 0;
 #pragma unroll 1
-        for (int idx = tid; idx < K2_ANG * Kp; idx += NC) {
+        for (int idx = tid; idx < sang * Kp; idx += NC) {
             const int ang = idx / Kp, kp = idx - ang * Kp;
             long long b = b0 + ang; if (b >= a.nb) b = a.nb - 1;
             double s, cs;
             sincos(sMu[kp] * a.beta[b], &s, &cs);         // fl(mu*beta) then sincos, like :199
             const double w = sW[kp];
-            const int row = k2_trig_row(ang);
+            const int row = (ang & ~(K2_ANG - 1)) + k2_trig_row(ang & (K2_ANG - 1));
             sTc[row * ldt + kp] = w * cs;
             sTs[row * ldt + kp] = w * s;
         }
@@ -500,7 +503,11 @@ __global__ void __launch_bounds__(k2_threads(CPLX), 1) k2_dmma_kernel(K2Args a)
             int v = 0;
             if (lane == 0) v = atomicAdd(sCounter, 1);
             v = __shfl_sync(0xffffffffu, v, 0);
-            if (v >= nunits) { if (cx.bar_other) named_bar_arrive(cx.bar_other, 64); break; }
+            if (v >= nunits * nsub_here) { if (cx.bar_other) named_bar_arrive(cx.bar_other, 64); break; }
+            const int sub = v / nunits;                            // which 16-angle chunk of the phase
+            v -= sub * nunits;
+            cx.b0 = b0 + sub * K2_ANG;
+            cx.sTc = sTc + sub * K2_ANG * ldt; cx.sTs = sTs + sub * K2_ANG * ldt;
             const int qn = v / upc, part = v - qn * upc;           // column-major unit order: see the store-locality note
             const int g0 = part * gbase + min(part, grem);
             const int gcnt = gbase + (part < grem ? 1 : 0);

@@ -139,6 +139,7 @@ struct K2Args {
     double *out;                          // nb * N*N doubles (or * 2 for complex)
     int equator;                          // apply the exact zeros of :230-237 (plain kernel only)
     int handoff;                          // DMMA kernel: midpoint hand-off between paired compute warps
+    int nsub;                             // DMMA kernel: 16-angle chunks per barrier phase (1 or 2)
 };
 
 template <bool CPLX>
