@@ -362,3 +362,84 @@ def test_full_size_cfg2_properties(engine):
     assert np.abs(d[pick].cpu().numpy() - ref).max() < TOL
     del d
     torch.cuda.empty_cache()
+
+
+# ---- edge cases -------------------------------------------------------------------------------------------
+def test_empty_and_single_batches(engine):
+    assert engine.wignerd_batch(3, np.zeros(0)).shape == (0, 7, 7)
+    assert engine.wignerD_batch(1.5, np.zeros(0), np.zeros(0), np.zeros(0)).shape == (0, 4, 4)
+    assert engine.wignerdjmn_batch(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0)).shape == (0,)
+    for twoj in (0, 1, 2, 201, 300):
+        d = engine.wignerd_batch(F(twoj, 2), np.array([1.234]))
+        assert np.abs(d[0] - o.wignerd_batch(F(twoj, 2), [1.234])[0]).max() < TOL
+
+
+def test_large_and_special_float_angles(engine):
+    # |mu*beta| ~ 1e7: both sides form fl(mu*beta) and call a full-range sincos, so they still agree
+    for beta in (1.0e6, -3.3e5, 12345.678):
+        for j in (2, 10.5):
+            assert np.abs(engine.wignerd_batch(j, [beta])[0] - o.wignerd_batch(j, [beta])[0]).max() < 1e-9
+    d = engine.wignerd_batch(2, np.array([np.nan, np.inf, 0.5]))
+    assert np.isnan(d[0]).all() and np.isnan(d[1]).all() and np.isfinite(d[2]).all()
+    assert np.abs(engine.wignerd(2, 0.0) - np.eye(5)).max() < 1e-15
+    assert np.array_equal(engine.wignerd(2, -0.0), engine.wignerd(2, 0.0))
+
+
+def test_shared_engine_from_threads(engine):
+    """one handle used from several threads: calls are serialised by the handle's mutex"""
+    errs = []
+
+    def work(seed):
+        rng = np.random.default_rng(seed)
+        for _ in range(10):
+            tj = int(rng.integers(0, 30))
+            b = rng.uniform(0, pi, 5)
+            if np.abs(engine.wignerd_batch(F(tj, 2), b) - o.wignerd_batch(F(tj, 2), b)).max() > 1e-13:
+                errs.append(tj)
+
+    ts = [threading.Thread(target=work, args=(s,)) for s in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs
+
+
+def test_device_memory_jmn_and_multi(engine):
+    import torch
+    dev = "cuda:0"
+    rng = np.random.default_rng(9)
+    n = 5000
+    tj = rng.integers(0, 51, n).astype(np.int32)
+    tm = (-tj + 2 * rng.integers(0, tj + 1)).astype(np.int32)
+    tn = (-tj + 2 * rng.integers(0, tj + 1)).astype(np.int32)
+    b = rng.uniform(0, pi, n)
+    out = engine.wignerdjmn_batch(torch.from_numpy(tj).to(dev), torch.from_numpy(tm).to(dev), torch.from_numpy(tn).to(dev),
+                                  torch.from_numpy(b).to(dev))
+    assert np.abs(out.cpu().numpy() - o.wignerdjmn_batch(tj, tm, tn, b)).max() < TOL
+    betas = torch.linspace(0.1, 3.0, 33, dtype=torch.float64, device=dev)
+    js = [0, 0.5, 1, 7, 10.5, 40]
+    _, _, views = engine.wignerd_multi(js, betas)
+    torch.cuda.synchronize()
+    for j, v in zip(js, views):
+        assert np.abs(v.cpu().numpy() - o.wignerd_batch(j, betas.cpu().numpy())).max() < 1e-13
+
+
+def test_prepare_and_cache_clear():
+    eng = w.Engine(0)
+    try:
+        eng.prepare(range(0, 41))
+        n0 = eng.launch_count()
+        a = eng.wignerd(10, 0.7)
+        eng.cache_clear()
+        b = eng.wignerd(10, 0.7)
+        assert np.array_equal(a, b) and eng.launch_count() > n0
+        u = eng.eigvecs(10)
+        assert np.abs(u.T @ u - np.eye(21)).max() < 1e-14
+    finally:
+        eng.close()
+
+
+def test_in_place_complex_poles(engine):
+    """wignerD! with NorthPole/SouthPole multiplies the caller's matrix by the phases after the pole fill (:335-342)"""
+    for sp, osp in ((w.NorthPole(), o.NorthPole()), (w.SouthPole(), o.SouthPole())):
+        D = engine.wignerD(2.5, 0.3, sp, 1.1)
+        assert np.abs(D - o.wignerD(2.5, 0.3, osp, 1.1)).max() < 1e-14

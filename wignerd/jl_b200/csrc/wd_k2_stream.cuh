@@ -91,24 +91,24 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // DMMAs of one mu chunk for one class: the two-fragment-set pipeline of k2_mainloop over nsteps k-steps.
-template <bool HALF, int GMAX>
+template <bool HALF, int GMAX, int GC>
 __device__ __forceinline__ void k2s_chunk(double (&acc)[2][GMAX][2][HALF ? 2 : 1][2], const double *tA, const double *tB,
                                           const double *un, const double *ub, const int nsteps)
 {
     constexpr int gs = 16 * K2S_LDU, t8 = 8 * K2S_LDT, ldu = K2S_LDU;
-    struct Frag { double un, ta[2], tb[2], be[GMAX], bo[GMAX]; };
+    struct Frag { double un, ta[2], tb[2], be[GC], bo[GC]; };
     auto load = [&](Frag &f, const int k) {
         f.un = un[k];
 #pragma unroll
         for (int ai = 0; ai < 2; ++ai) { f.ta[ai] = tA[ai * t8 + k]; f.tb[ai] = tB[ai * t8 + k]; }
 #pragma unroll
-        for (int g = 0; g < GMAX; ++g) { f.be[g] = ub[g * gs + k]; f.bo[g] = ub[g * gs + ldu + k]; }
+        for (int g = 0; g < GC; ++g) { f.be[g] = ub[g * gs + k]; f.bo[g] = ub[g * gs + ldu + k]; }
     };
     auto step = [&](Frag &f) {
 #pragma unroll
         for (int ai = 0; ai < 2; ++ai) { f.ta[ai] *= f.un; f.tb[ai] *= f.un; }
 #pragma unroll
-        for (int g = 0; g < GMAX; ++g) {
+        for (int g = 0; g < GC; ++g) {
 #pragma unroll
             for (int ai = 0; ai < 2; ++ai) {
                 dmma(acc[ai][g][0][0], f.ta[ai], f.be[g]);
@@ -234,8 +234,14 @@ __global__ void __launch_bounds__(k2_threads(false), 1) k2_stream_kernel(K2SArgs
                 const double *tA = pe ? ts : tc, *tB = pe ? tc : ts;
                 const double *un = st + L.uqc + warp * K2S_LDU + c;
                 const double *ub = st + L.uqr + (2 * r) * K2S_LDU + c;
-                if (cls == 0) k2s_chunk<HALF, GMAX>(acc[0], tA, tB, un, ub, nsteps);
-                else k2s_chunk<HALF, GMAX>(acc[1], tA, tB, un, ub, nsteps);
+                // only the 16-row groups that exist in this row block issue DMMAs (the last block of a column is partial)
+                auto run = [&](double (&ac)[2][GMAX][2][NALT][2]) {
+                    if (gcnt == GMAX) k2s_chunk<HALF, GMAX, GMAX>(ac, tA, tB, un, ub, nsteps);
+                    else if (gcnt == 1) k2s_chunk<HALF, GMAX, 1>(ac, tA, tB, un, ub, nsteps);
+                    else if (gcnt == 2) k2s_chunk<HALF, GMAX, (GMAX >= 2 ? 2 : 1)>(ac, tA, tB, un, ub, nsteps);
+                    else k2s_chunk<HALF, GMAX, (GMAX >= 3 ? 3 : 1)>(ac, tA, tB, un, ub, nsteps);
+                };
+                if (cls == 0) run(acc[0]); else run(acc[1]);
             }
         }
         if (!active) continue;
