@@ -103,7 +103,8 @@ struct K2Desc {
     unsigned long long e00;     // element index of (angle 0 of the chunk, staging position 0)
     int s_lo, s_hi;             // valid staging positions; s_hi < 0: the compute warp has finished
     int nrows0, nrows1;         // existing angles of tile 0 (even angles) / tile 1 (odd angles)
-    int pad[2];
+    int dib;                    // row - col of staging position 0 (mod 4): the store warp applies sigma(dib + s)
+    int pad;
 };
 
 struct K2Smem {                 // offsets in doubles, computed identically on host and device
@@ -216,6 +217,7 @@ __device__ __forceinline__ void k2_drain_real(const double *buf, double *out, co
         if (s < d.s_lo || s >= d.s_hi) continue;
         const double *src = buf + s;
         double *dst = out + d.e00 + s;
+        const unsigned sb = sigma_bit(d.dib + s);                      // sign sigma(row - col) of this output row
 #pragma unroll
         for (int ai = 0; ai < 2; ++ai) {
             const int nrows = ai ? d.nrows1 : d.nrows0;
@@ -226,9 +228,9 @@ __device__ __forceinline__ void k2_drain_real(const double *buf, double *out, co
 #pragma unroll
                 for (int ar = 0; ar < 8; ++ar) v[ar] = sp[ar * K2_STG_LD];
 #pragma unroll
-                for (int ar = 0; ar < 8; ++ar) dp[(size_t)(2 * ar) * NN] = v[ar];
+                for (int ar = 0; ar < 8; ++ar) dp[(size_t)(2 * ar) * NN] = flip(v[ar], sb);
             } else {
-                for (int ar = 0; ar < nrows; ++ar) dp[(size_t)(2 * ar) * NN] = sp[ar * K2_STG_LD];
+                for (int ar = 0; ar < nrows; ++ar) dp[(size_t)(2 * ar) * NN] = flip(sp[ar * K2_STG_LD], sb);
             }
         }
     }
@@ -266,7 +268,7 @@ __device__ __forceinline__ void k2_store_target(const K2Args &a, K2Ctx &cx, cons
             d.e00 = e00; d.s_lo = s_lo; d.s_hi = s_hi;
             d.nrows0 = (int)max(0LL, min(8LL, (a.nb - cx.b0 + 1) / 2));
             d.nrows1 = (int)max(0LL, min(8LL, (a.nb - cx.b0) / 2));
-            d.pad[0] = d.pad[1] = 0;
+            d.dib = (row0 - col) & 3; d.pad = 0;
             *cx.desc = d;
         }
     } else {
@@ -278,8 +280,11 @@ __device__ __forceinline__ void k2_store_target(const K2Args &a, K2Ctx &cx, cons
         for (int g = 0; g < GMAX; ++g) {
             if (g < gcnt) {
                 // the lane owns rows 16g+4c .. 16g+4c+3 of the unit: (even tile, odd tile) interleaved
-                const double v0 = flip(val[ai][g][0][0], sb[0]), v1 = flip(val[ai][g][1][0], sb[1]);
-                const double v2 = flip(val[ai][g][0][1], sb[2]), v3 = flip(val[ai][g][1][1], sb[3]);
+                // (real d: the store warp applies the sign sigma; complex D: applied here)
+                const double v0 = CPLX ? flip(val[ai][g][0][0], sb[0]) : val[ai][g][0][0];
+                const double v1 = CPLX ? flip(val[ai][g][1][0], sb[1]) : val[ai][g][1][0];
+                const double v2 = CPLX ? flip(val[ai][g][0][1], sb[2]) : val[ai][g][0][1];
+                const double v3 = CPLX ? flip(val[ai][g][1][1], sb[3]) : val[ai][g][1][1];
                 double *p = buf + (ai * 8 + r) * K2_STG_LD + (DESC ? (span - 4) - 16 * g - 4 * c : 16 * g + 4 * c);
                 reinterpret_cast<double2 *>(p)[0] = DESC ? make_double2(v3, v2) : make_double2(v0, v1);
                 reinterpret_cast<double2 *>(p)[1] = DESC ? make_double2(v1, v0) : make_double2(v2, v3);
@@ -519,7 +524,7 @@ __global__ void __launch_bounds__(k2_threads(CPLX), 1) k2_dmma_kernel(K2Args a)
         mbar_wait(cx.empty, (cx.tiles & 1) ^ 1);
         if (lane == 0) {
             K2Desc d;
-            d.e00 = 0; d.s_lo = 0; d.s_hi = -1; d.nrows0 = d.nrows1 = 0; d.pad[0] = d.pad[1] = 0;
+            d.e00 = 0; d.s_lo = 0; d.s_hi = -1; d.nrows0 = d.nrows1 = 0; d.dib = 0; d.pad = 0;
             *cx.desc = d;
         }
         __syncwarp();

@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(k2_threads(false), 1) k2_stream_kernel(K2SArgs
     mbar_wait(cx.empty, (cx.tiles & 1) ^ 1);
     if (lane == 0) {
         K2Desc d;
-        d.e00 = 0; d.s_lo = 0; d.s_hi = -1; d.nrows0 = d.nrows1 = 0; d.pad[0] = d.pad[1] = 0;
+        d.e00 = 0; d.s_lo = 0; d.s_hi = -1; d.nrows0 = d.nrows1 = 0; d.dib = 0; d.pad = 0;
         *cx.desc = d;
     }
     __syncwarp();
