@@ -238,10 +238,15 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
     a.alpha = alpha; a.beta = beta; a.gamma = gamma;
     a.nb = nb; a.out = out; a.equator = equator ? 1 : 0;
     {
+        // hand-off between the two compute warps of a sub-partition: the partner is released when ~80 % of the k-steps
+        // of a main loop are done (measured at cfg-2: release at 50 % 10.7 ms, 80 % 10.1 ms, 100 % 11.0 ms, off 11.4 ms).
+        // Encoding: 0 = off; h = release after h-1 pairs of k-steps of class 0, or (h-1 >= 100) h-101 pairs of class 1.
+        const int s0 = pl.dev.K0p / 4, s1 = pl.dev.K1p / 4;
+        const int target = (4 * (s0 + s1) + 4) / 5;
+        a.handoff = 1 + (target <= s0 ? target / 2 : 100 + (target - s0) / 2);
         const char *e = getenv("WD_K2_HANDOFF");        // kernel-experiment knob
-        a.handoff = e ? atoi(e) : 1;
+        if (e) a.handoff = atoi(e);
     }
-    size_t smem = 0;
     // two 16-angle chunks per barrier phase measured no gain (10.98 vs 11.25 ms at cfg-2): one chunk unless asked for
     int nsub_max = 1;
     {
@@ -249,6 +254,7 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
         if (e && atoi(e) == 2) nsub_max = 2;
     }
     int nsub = 1;
+    size_t smem = 0;
     const bool fits = dmma_fits(h, pl.dev, cplx, &smem, &nsub, nsub_max);
     a.nsub = nsub;
     int variant = h->variant;

@@ -139,7 +139,8 @@ struct K2Ctx {                  // per-thread constants of a compute warp
     int ldu, ldt, N, Q, i0, zskip, Kp, K0p, twoj;
     int lane, r, c;
     unsigned tiles;             // tiles handed to the store warp so far (mbarrier phase)
-    int bar_me, bar_other;      // named barriers of the midpoint hand-off between the two warps of a sub-partition (0 = off)
+    int bar_me, bar_other;      // named barriers of the hand-off between the two warps of a sub-partition (0 = off)
+    int krel;                   // release point: after this many pairs of k-steps of the first class
     long long b0;
 };
 
@@ -194,15 +195,21 @@ __device__ __forceinline__ void k2_mainloop(double (&acc)[2][2][GMAX][2][HALF ? 
         Frag f0, f1;
         load(f0, kbeg);
         int k = kbeg;
+        // hand-off: the partner warp is released after cx.krel pairs of k-steps of class 0 (or at its end)
+        // (krel >= 100: in class 1, after krel - 100 pairs)
+        const int krel = !cx.bar_other ? -1 : (cls == 0 ? (cx.krel < 100 ? kbeg + 8 * cx.krel : -1)
+                                                           : (cx.krel >= 100 ? kbeg + 8 * (cx.krel - 100) : -1));
+        bool released = false;
 #pragma unroll 1
         for (; k + 4 < kend; k += 8) {
+            if (k == krel) { named_bar_arrive(cx.bar_other, 64); released = true; }
             load(f1, k + 4);
             step(f0);
             load(f0, k + 8);
             step(f1);
         }
         if (k < kend) step(f0);
-        if (cls == 0 && cx.bar_other) named_bar_arrive(cx.bar_other, 64);     // midpoint: release the partner warp
+        if (cx.bar_other && !released && ((cls == 0 && cx.krel < 100) || (cls == 1 && cx.krel >= 100))) named_bar_arrive(cx.bar_other, 64);
     }
 }
 
@@ -455,6 +462,7 @@ __global__ void __launch_bounds__(k2_threads(CPLX), 1) k2_dmma_kernel(K2Args a)
     // named barriers), so the main loops overlap pairwise by half and the epilogues of the pair never coincide.
     // (Left alone the pair locks into phase: the warp that is alone in its main loop runs faster than half speed, so
     // any offset shrinks, and then both are in their epilogues while the pipe idles.)  Measured: 11.4 -> 10.7 ms.
+    cx.krel = a.handoff - 1;
     cx.bar_me = a.handoff ? 2 + warp : 0;
     cx.bar_other = a.handoff ? 2 + (warp ^ 4) : 0;
     if (a.handoff && (warp & 4)) named_bar_arrive(cx.bar_other, 64);       // warps 0..3 take the first turn
