@@ -187,8 +187,11 @@ int launch_dmma(wd_handle_t h, const K2Args &a, size_t smem)
         h->attr_set[HALF][CPLX] = true;
     }
     const long long nchunks = (a.nb + K2_ANG * a.nsub - 1) / (K2_ANG * a.nsub);
-    const int grid = (int)std::min<long long>(nchunks, h->num_sms);
-    k2_dmma_kernel<HALF, CPLX><<<grid, k2_threads(CPLX), smem, h->stream>>>(a);
+    // fewer chunks than SMs: split every chunk's units over several CTAs (each rebuilds the chunk's small trig tables)
+    K2Args b = a;
+    b.nsplit = nchunks >= h->num_sms ? 1 : (int)std::min<long long>(16, (h->num_sms + nchunks - 1) / nchunks);
+    const int grid = (int)std::min<long long>(nchunks * b.nsplit, h->num_sms);
+    k2_dmma_kernel<HALF, CPLX><<<grid, k2_threads(CPLX), smem, h->stream>>>(b);
     h->launches++;
     CU(cudaGetLastError());
     return WD_OK;

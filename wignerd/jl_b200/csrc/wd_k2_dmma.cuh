@@ -474,12 +474,18 @@ __global__ void __launch_bounds__(k2_threads(CPLX), 1) k2_dmma_kernel(K2Args a)
     const int sang = K2_ANG * nsub;                        // angles per barrier phase
     const long long nchunks = (a.nb + sang - 1) / sang;
 
-    for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    // work item = (chunk, split): small batches are split over several CTAs per chunk so that the whole GPU is used
+    const int nsplit = max(1, a.nsplit);
+    for (long long item = blockIdx.x; item < nchunks * nsplit; item += gridDim.x) {
+        const long long ch = item / nsplit;
+        const int split = (int)(item - ch * nsplit);
         const long long b0 = ch * sang;
         const int nsub_here = (int)min((long long)nsub, (a.nb - b0 + K2_ANG - 1) / K2_ANG);
         cx.b0 = b0;
         named_bar_sync(1, NC);                             // compute warps: previous chunk's table readers are done
-        if (tid == 0) *sCounter = 0;
+        const int ntot = nunits * nsub_here;
+        const int u_begin = (int)((long long)ntot * split / nsplit), u_end = (int)((long long)ntot * (split + 1) / nsplit);
+        if (tid == 0) *sCounter = u_begin;
 #pragma unroll 1
         for (int idx = tid; idx < sang * Kp; idx += NC) {
             const int ang = idx / Kp, kp = idx - ang * Kp;
@@ -516,7 +522,7 @@ __global__ void __launch_bounds__(k2_threads(CPLX), 1) k2_dmma_kernel(K2Args a)
             int v = 0;
             if (lane == 0) v = atomicAdd(sCounter, 1);
             v = __shfl_sync(0xffffffffu, v, 0);
-            if (v >= nunits * nsub_here) { if (cx.bar_other) named_bar_arrive(cx.bar_other, 64); break; }
+            if (v >= u_end) { if (cx.bar_other) named_bar_arrive(cx.bar_other, 64); break; }
             const int sub = v / nunits;                            // which 16-angle chunk of the phase
             v -= sub * nunits;
             cx.b0 = b0 + sub * K2_ANG;

@@ -140,6 +140,7 @@ struct K2Args {
     int equator;                          // apply the exact zeros of :230-237 (plain kernel only)
     int handoff;                          // DMMA kernel: midpoint hand-off between paired compute warps
     int nsub;                             // DMMA kernel: 16-angle chunks per barrier phase (1 or 2)
+    int nsplit;                           // DMMA kernel: CTAs per chunk (small batches)
 };
 
 template <bool CPLX>
