@@ -346,7 +346,9 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg["desc"], "name": args.config, "twoj": twoj, "angles_per_gpu": nb,
                    "output_bytes_per_gpu": bytes_per_launch, "l2": "outputs (>=16 GB per step) far exceed the 126 MB L2; no flush needed",
-                   "variant": args.variant, "e2e_angles_per_gpu": ne},
+                   "variant": args.variant, "e2e_angles_per_gpu": ne,
+                   "inputs": ("alpha, gamma ~ U[0, 2pi), beta ~ U[0, pi], torch.Generator(cuda).manual_seed(2 + rank)" if cplx
+                              else "beta = rank's slab of linspace(0, pi, n_gpus * angles_per_gpu)")},
         "clocks": clocks,
         "e2e": {"value": e2e_rate, "unit": "elements/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "note": "wd_d_batch with pinned HOST buffers; PCIe copies inside the timed region"},
@@ -376,9 +378,12 @@ def main():
         try:
             nang = 512 if twoj >= 150 else 4096
             rate, threads, dt_cpu = cpu_port_rate(twoj, nang, 0, kind=cfg["kind"])
+            n1 = max(8, nang // 32)
+            rate1, _, dt1 = cpu_port_rate(twoj, n1, 1, kind=cfg["kind"])
             line["cpu_baseline"] = {"value": rate, "unit": "elements/s", "cores": threads, "kind": "port",
                                     "sample": f"{nang} of {nb} angles, {dt_cpu:.2f} s wall on {threads} host threads "
-                                              "(C port of the reference loop, oracle/wignerd_ref.c; Julia absent)"}
+                                              "(C port of the reference loop, oracle/wignerd_ref.c; Julia absent)",
+                                    "value_1thread": rate1, "sample_1thread": f"{n1} angles, {dt1:.2f} s on 1 thread"}
         except Exception as e:      # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": "elements/s", "cores": 0, "kind": "port", "sample": repr(e)}
     print(json.dumps(line), flush=True)
