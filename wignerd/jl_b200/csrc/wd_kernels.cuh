@@ -254,11 +254,18 @@ __global__ void __launch_bounds__(256) k4_jmn_kernel(K4Args a)
             const bool odd = (i - ip) & 1;
             const double *um = p.uq + (size_t)qm * p.ldu, *un = p.uq + (size_t)qn * p.ldu;
             double s0 = 0.0, s1 = 0.0;
+            // mu and w of column kp are recomputed from the index (same arithmetic as k1_eig_kernel) instead of being
+            // read: the kernel is bound by L2 reads of the two table rows
+            const int K = p.Q, c0 = (K - 1) & 1, par = p.twoj & 1;
             for (int kp = lane; kp < p.Kp; kp += 32) {
-                double s, c;
-                sincos(p.mu[kp] * beta, &s, &c);
-                const double g = p.w[kp] * (odd ? s : c) * (um[kp] * un[kp]);
-                if (kp < p.K0p) s0 += g; else s1 += g;
+                const bool cls1 = kp >= p.K0p;
+                const int t = cls1 ? kp - p.K0p : kp;
+                if (t >= (cls1 ? p.K1 : p.K0)) continue;             // pad column
+                const int kappa = (cls1 ? (c0 ^ 1) : c0) + 2 * t;
+                const double mu = 0.5 * (double)(2 * kappa + par);
+                const double tr = odd ? sin(mu * beta) : cos(mu * beta);     // (warp-uniform choice: one function, not sincos)
+                const double g = ((kappa | par) ? 2.0 : 1.0) * tr * (um[kp] * un[kp]);
+                if (cls1) s1 += g; else s0 += g;
             }
             double x = flip1 ? (s0 - s1) : (s0 + s1);
 #pragma unroll
