@@ -65,7 +65,7 @@ def test_ref_cartesian(engine):
 
 
 # ---- spectral setup (K1) --------------------------------------------------------------------------------
-@pytest.mark.parametrize("twoj", [0, 1, 2, 3, 20, 99, 200, 401, 1024])
+@pytest.mark.parametrize("twoj", [0, 1, 2, 3, 20, 99, 200, 401, 1024, 1100, 2001])
 def test_eigvecs_residual_orthogonality(engine, twoj):
     u = engine.eigvecs(F(twoj, 2))
     N = twoj + 1
@@ -73,7 +73,7 @@ def test_eigvecs_residual_orthogonality(engine, twoj):
     b = 0.5 * np.sqrt(k * (N - k))
     T = np.diag(b, 1) + np.diag(b, -1)
     lam = np.arange(N) - twoj / 2
-    assert np.abs(T @ u - u * lam).max() < 2e-13 * max(1.0, twoj / 200)
+    assert np.abs(T @ u - u * lam).max() < 2e-13 * max(1.0, twoj / 200)      # ~ eps * ||T||
     assert np.abs(u.T @ u - np.eye(N)).max() < 1e-13
     # same subspaces as LAPACK zheevr on the reference's own J_y: |<m|mu>| agree
     if twoj <= 200:
@@ -443,3 +443,19 @@ def test_in_place_complex_poles(engine):
     for sp, osp in ((w.NorthPole(), o.NorthPole()), (w.SouthPole(), o.SouthPole())):
         D = engine.wignerD(2.5, 0.3, sp, 1.1)
         assert np.abs(D - o.wignerD(2.5, 0.3, osp, 1.1)).max() < 1e-14
+
+
+@pytest.mark.parametrize("twoj", [1100, 1401, 2000])
+def test_very_large_j_invariants(engine, twoj):
+    """beyond 2j ~ 1024 the eigenvector tails underflow 2^-j: the twist index must stay in the classically allowed
+    region (regression test).  The oracle needs minutes here, so the size-independent properties are checked."""
+    j = F(twoj, 2)
+    N = twoj + 1
+    betas = np.array([0.7, 2.9])
+    d = engine.wignerd_batch(j, betas)
+    m = np.arange(N) - twoj / 2
+    for b, db in zip(betas, d):
+        assert np.abs(db.T @ db - np.eye(N)).max() < 1e-12
+        assert abs(np.trace(db) - np.cos(m * b).sum()) < 1e-11
+    dm = engine.wignerd_batch(j, -betas)
+    assert np.abs(dm.transpose(0, 2, 1) - d).max() < 1e-12

@@ -91,10 +91,16 @@ __global__ void __launch_bounds__(128) k1_eig_kernel(const EigJob *__restrict__ 
         if (fabs(d) < pivmin) d = -pivmin;
         Dp[(size_t)(i + 1) * K] = d;
     }
-    // twist index: argmin |gamma_r|, gamma_r = D+[r] + D-[r] + lam
-    int r = 0;
+    // twist index: argmin |gamma_r|, gamma_r = D+[r] + D-[r] + lam -- restricted to the classically allowed region
+    // |m| <= sqrt(j(j+1) - mu^2) + 1, where the eigenvector is O(1).  With the EXACT eigenvalue every gamma_r is pure
+    // roundoff and may vanish in the exponentially small tails (|z| ~ 2^-j); twisting there makes the recurrence grow
+    // by 2^j and z^2 overflows for 2j > ~1024.
+    const double jj1 = 0.25 * (double)jb.twoj * (double)(jb.twoj + 2);
+    const double mt = sqrt(fmax(0.0, jj1 - lam * lam)) + 1.0;
+    const int i_lo = max(0, (int)ceil(0.5 * jb.twoj - mt)), i_hi = min(N - 1, (int)floor(0.5 * jb.twoj + mt));
+    int r = (i_lo + i_hi) >> 1;
     double best = 1.7976931348623157e308;
-    for (int i = 0; i < N; ++i) {
+    for (int i = i_lo; i <= i_hi; ++i) {
         const double g = fabs(Dp[(size_t)i * K] + Dp[(size_t)(N - 1 - i) * K] + lam);
         if (g < best) { best = g; r = i; }
     }
