@@ -240,6 +240,11 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
     a.p = pl.dev;
     a.alpha = alpha; a.beta = beta; a.gamma = gamma;
     a.nb = nb; a.out = out; a.equator = equator ? 1 : 0;
+    a.nsplit = 1; a.wrap = 0;
+    {
+        const char *e = getenv("WD_K2_WRAP");            // kernel-experiment knob: output index modulo this many doubles
+        if (e) a.wrap = strtoull(e, nullptr, 10);
+    }
     {
         // hand-off between the two compute warps of a sub-partition: the partner is released when ~80 % of the k-steps
         // of a main loop are done (measured at cfg-2: release at 50 % 10.7 ms, 80 % 10.1 ms, 100 % 11.0 ms, off 11.4 ms).

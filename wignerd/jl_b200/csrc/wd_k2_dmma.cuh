@@ -109,7 +109,7 @@ struct K2Desc {
 
 struct K2Smem {                 // offsets in doubles, computed identically on host and device
     int uq, mu, w, tc, ts, ph, stg, desc, bars, total;
-    int ldt, qpad;
+    int ldt, qpad, stg_rows;
 };
 __host__ __device__ inline K2Smem k2_smem_layout(int Q, int Kp, int ldu, bool cplx, int nsub = 1)
 {
@@ -124,7 +124,8 @@ __host__ __device__ inline K2Smem k2_smem_layout(int Q, int Kp, int ldu, bool cp
     s.ts = o;  o += nsub * K2_ANG * s.ldt;
     s.ph = o;  o += cplx ? 4 * K2_ANG * Q : 0;          // cos(m a), sin(m a), cos(n g), sin(n g)  [16][Q]
     o = (o + 1) & ~1;
-    s.stg = o;  o += K2_CWARPS * K2_STG_ROWS * K2_STG_LD;
+    s.stg_rows = cplx ? 8 : K2_STG_ROWS;       // complex D stages one angle tile at a time (room for the phase tables)
+    s.stg = o;  o += K2_CWARPS * s.stg_rows * K2_STG_LD;
     s.desc = o; o += K2_CWARPS * (int)(sizeof(K2Desc) / 8);
     s.bars = o; o += 2 * K2_CWARPS + 2;                 // full[8], empty[8], UQ-load barrier, unit counter
     s.total = o;
@@ -266,9 +267,10 @@ __device__ __forceinline__ void k2_store_target(const K2Args &a, K2Ctx &cx, cons
 #pragma unroll
     for (int t = 0; t < 4; ++t) sb[t] = sigma_bit(DESC ? dib - t : dib + t);
     const size_t NN = (size_t)N * N;
-    const size_t e00 = (size_t)cx.b0 * NN + (size_t)col * N + row0;   // angle 0 of the chunk, staging position 0
+    size_t e00 = (size_t)cx.b0 * NN + (size_t)col * N + row0;         // angle 0 of the chunk, staging position 0
+    if (a.wrap) e00 %= a.wrap;                                        // experiment knob: SM-side time without DRAM writes
     double *buf = cx.stg;
-    if (!CPLX) {
+    if constexpr (!CPLX) {
         mbar_wait(cx.empty, (cx.tiles & 1) ^ 1);                     // the store warp has drained the previous tile
         if (lane == 0) {
             K2Desc d;
@@ -278,49 +280,53 @@ __device__ __forceinline__ void k2_store_target(const K2Args &a, K2Ctx &cx, cons
             d.dib = (row0 - col) & 3; d.pad = 0;
             *cx.desc = d;
         }
-    } else {
+#pragma unroll
+        for (int ai = 0; ai < 2; ++ai) {
+#pragma unroll
+            for (int g = 0; g < GMAX; ++g) {
+                if (g < gcnt) {
+                    // the lane owns rows 16g+4c .. 16g+4c+3 of the unit: (even tile, odd tile) interleaved; the store
+                    // warp applies the sign sigma
+                    const double v0 = val[ai][g][0][0], v1 = val[ai][g][1][0], v2 = val[ai][g][0][1], v3 = val[ai][g][1][1];
+                    double *p = buf + (ai * 8 + r) * K2_STG_LD + (DESC ? (span - 4) - 16 * g - 4 * c : 16 * g + 4 * c);
+                    reinterpret_cast<double2 *>(p)[0] = DESC ? make_double2(v3, v2) : make_double2(v0, v1);
+                    reinterpret_cast<double2 *>(p)[1] = DESC ? make_double2(v1, v0) : make_double2(v2, v3);
+                }
+            }
+        }
         __syncwarp();
-    }
+        if (lane == 0) mbar_arrive(cx.full);                          // release: tile + descriptor are visible
+        ++cx.tiles;
+    } else {
+    // complex D: one angle tile (8 rows) at a time: stage with the sign applied, then drain with the fused phase
+    // exp(-i(m alpha + n gamma)) = (ca - i sa)(cg - i sg); m -> -m flips sa, n -> -n flips sg
 #pragma unroll
     for (int ai = 0; ai < 2; ++ai) {
+        const long long bfirst = cx.b0 + ai;
+        if (bfirst >= a.nb) break;                                    // warp-uniform
+        const int nrows = (int)min(8LL, (a.nb - bfirst + 1) / 2);
+        __syncwarp();
 #pragma unroll
         for (int g = 0; g < GMAX; ++g) {
             if (g < gcnt) {
-                // the lane owns rows 16g+4c .. 16g+4c+3 of the unit: (even tile, odd tile) interleaved
-                // (real d: the store warp applies the sign sigma; complex D: applied here)
-                const double v0 = CPLX ? flip(val[ai][g][0][0], sb[0]) : val[ai][g][0][0];
-                const double v1 = CPLX ? flip(val[ai][g][1][0], sb[1]) : val[ai][g][1][0];
-                const double v2 = CPLX ? flip(val[ai][g][0][1], sb[2]) : val[ai][g][0][1];
-                const double v3 = CPLX ? flip(val[ai][g][1][1], sb[3]) : val[ai][g][1][1];
-                double *p = buf + (ai * 8 + r) * K2_STG_LD + (DESC ? (span - 4) - 16 * g - 4 * c : 16 * g + 4 * c);
+                const double v0 = flip(val[ai][g][0][0], sb[0]), v1 = flip(val[ai][g][1][0], sb[1]);
+                const double v2 = flip(val[ai][g][0][1], sb[2]), v3 = flip(val[ai][g][1][1], sb[3]);
+                double *p = buf + r * K2_STG_LD + (DESC ? (span - 4) - 16 * g - 4 * c : 16 * g + 4 * c);
                 reinterpret_cast<double2 *>(p)[0] = DESC ? make_double2(v3, v2) : make_double2(v0, v1);
                 reinterpret_cast<double2 *>(p)[1] = DESC ? make_double2(v1, v0) : make_double2(v2, v3);
             }
         }
-    }
-    __syncwarp();
-    if (!CPLX) {
-        if (lane == 0) mbar_arrive(cx.full);                          // release: tile + descriptor are visible
-        ++cx.tiles;
-        return;
-    }
-    // complex D: exp(-i(m alpha + n gamma)) = (ca - i sa)(cg - i sg); m -> -m flips sa, n -> -n flips sg
+        __syncwarp();
 #pragma unroll 1
-    for (int hh = 0; hh * 32 < span; ++hh) {
-        const int s = hh * 32 + lane;
-        if (s < s_lo || s >= s_hi) continue;
-        const double *src = buf + s;
-        const int row = row0 + s;
-        const bool mneg = row < i0, nneg = col < i0;
-        const int qr = mneg ? (N - 1 - row - i0) : (row - i0);
-        const int qc = nneg ? (N - 1 - col - i0) : (col - i0);
-#pragma unroll
-        for (int ai = 0; ai < 2; ++ai) {
-            const long long bfirst = cx.b0 + ai;
-            if (bfirst >= a.nb) break;                                // warp-uniform
-            const int nrows = (int)min(8LL, (a.nb - bfirst + 1) / 2);
+        for (int hh = 0; hh * 32 < span; ++hh) {
+            const int s = hh * 32 + lane;
+            if (s < s_lo || s >= s_hi) continue;
+            const int row = row0 + s;
+            const bool mneg = row < i0, nneg = col < i0;
+            const int qr = mneg ? (N - 1 - row - i0) : (row - i0);
+            const int qc = nneg ? (N - 1 - col - i0) : (col - i0);
             const double *pa = cx.sPh + ai * Q + qr, *pg = cx.sPh + (2 * K2_ANG + ai) * Q + qc;
-            const double *sp = src + ai * 8 * K2_STG_LD;
+            const double *sp = buf + s;
             double2 *dst = reinterpret_cast<double2 *>(a.out) + e00 + (size_t)ai * NN + s;
 #pragma unroll 2
             for (int ar = 0; ar < nrows; ++ar) {                      // angle 2 ar + ai of the chunk
@@ -334,6 +340,7 @@ __device__ __forceinline__ void k2_store_target(const K2Args &a, K2Ctx &cx, cons
                 dst[(size_t)(2 * ar) * NN] = make_double2(v * cr, v * ci);
             }
         }
+    }
     }
 }
 
@@ -450,7 +457,7 @@ __global__ void __launch_bounds__(k2_threads(CPLX), 1) k2_dmma_kernel(K2Args a)
 
     K2Ctx cx;
     cx.sUQ = sUQ; cx.sTc = sTc; cx.sTs = sTs; cx.sPh = sPh;
-    cx.stg = sm + L.stg + warp * (K2_STG_ROWS * K2_STG_LD);
+    cx.stg = sm + L.stg + warp * (L.stg_rows * K2_STG_LD);
     cx.desc = reinterpret_cast<K2Desc *>(sm + L.desc + warp * (int)(sizeof(K2Desc) / 8));
     cx.full = sm + L.bars + warp; cx.empty = sm + L.bars + K2_CWARPS + warp;
     cx.ldu = ldu; cx.ldt = ldt; cx.N = p.N; cx.Q = Q; cx.i0 = p.N - Q; cx.zskip = p.zskip;
