@@ -67,6 +67,7 @@ struct wd_handle_s {
     int *d_flag = nullptr;           // error flag / scratch ints
     bool attr_set[2][2] = {{false, false}, {false, false}};
     bool attr_set_stream[2] = {false, false};
+    bool attr_set_real[2] = {false, false};
     // host-path workspace, kept across calls (grow-only): angle vectors and two output slabs + their events
     double *ws_ang = nullptr, *ws_slab[2] = {nullptr, nullptr};
     size_t ws_ang_bytes = 0, ws_slab_bytes[2] = {0, 0};
@@ -197,6 +198,41 @@ int launch_dmma(wd_handle_t h, const K2Args &a, size_t smem)
     return WD_OK;
 }
 
+// Resident DMMA kernel for real d (second generation: k2_real_kernel)
+bool real_fits(wd_handle_t h, const PlanDev &p, size_t *bytes)
+{
+    const K2RSmem L = k2r_smem_layout(p.Q, p.Kp, p.ldu);
+    *bytes = (size_t)L.total * sizeof(double);
+    return *bytes <= h->smem_optin;
+}
+
+template <bool HALF>
+int launch_real(wd_handle_t h, const K2Args &a, size_t smem)
+{
+    if (!h->attr_set_real[HALF]) {
+        CU(cudaFuncSetAttribute(k2_real_kernel<HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+        h->attr_set_real[HALF] = true;
+    }
+    // items: whole chunks of 16 angles for every full wave of the grid; the chunks of the last, partial wave (or of a
+    // batch smaller than the GPU) are split over several CTAs each (every CTA rebuilds the chunk's small trig tables)
+    K2Args b = a;
+    const long long G = h->num_sms;
+    const long long nchunks = (a.nb + K2_ANG - 1) / K2_ANG;
+    b.nfull = (nchunks / G) * G;
+    const long long rem = nchunks - b.nfull;
+    b.tsplit = rem ? (int)std::max<long long>(1, std::min<long long>(16, G / rem)) : 1;
+    {
+        const char *e = getenv("WD_K2_TAIL");             // kernel-experiment knob: 0 = never split the last wave
+        if (e && atoi(e) == 0 && b.nfull > 0) b.tsplit = 1;
+    }
+    b.nitems = b.nfull + rem * b.tsplit;
+    const int grid = (int)std::min<long long>(b.nitems, G);
+    k2_real_kernel<HALF><<<grid, k2_threads(false), smem, h->stream>>>(b);
+    h->launches++;
+    CU(cudaGetLastError());
+    return WD_OK;
+}
+
 // Streaming DMMA kernel (real d, table too large for shared memory): trig table pass + contraction.
 template <bool HALF>
 int launch_stream(wd_handle_t h, const K2Args &a)
@@ -240,7 +276,7 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
     a.p = pl.dev;
     a.alpha = alpha; a.beta = beta; a.gamma = gamma;
     a.nb = nb; a.out = out; a.equator = equator ? 1 : 0;
-    a.nsplit = 1; a.wrap = 0;
+    a.nsplit = 1; a.wrap = 0; a.nfull = 0; a.nitems = 0; a.tsplit = 1;
     {
         const char *e = getenv("WD_K2_WRAP");            // kernel-experiment knob: output index modulo this many doubles
         if (e) a.wrap = strtoull(e, nullptr, 10);
@@ -263,14 +299,18 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
     }
     int nsub = 1;
     size_t smem = 0;
-    const bool fits = dmma_fits(h, pl.dev, cplx, &smem, &nsub, nsub_max);
+    bool fits = dmma_fits(h, pl.dev, cplx, &smem, &nsub, nsub_max);
     a.nsub = nsub;
-    int variant = h->variant;
+    // real d: the second-generation kernel (variant 4 = the first-generation one, kept for A/B measurements)
+    const bool gen2 = !cplx && h->variant != 4;
+    if (gen2) fits = real_fits(h, pl.dev, &smem);
+    int variant = h->variant == 4 ? 2 : h->variant;
     if (variant == 2 && !fits) return fail(WD_ERR_UNSUPPORTED, "2j = %d does not fit the DMMA kernel (%zu B of shared memory)", pl.dev.twoj, smem);
     // Equator() requests (single matrices, exact zeros of :230-237) take the plain kernel
     if (variant == 3 && !cplx && !equator) return (pl.dev.twoj & 1) ? launch_stream<true>(h, a) : launch_stream<false>(h, a);
     const bool use_dmma = !equator && ((variant == 2) || (variant == 0 && fits));
     const bool half = pl.dev.twoj & 1;
+    if (use_dmma && gen2) return half ? launch_real<true>(h, a, smem) : launch_real<false>(h, a, smem);
     if (use_dmma) {
         if (half) return cplx ? launch_dmma<true, true>(h, a, smem) : launch_dmma<true, false>(h, a, smem);
         return cplx ? launch_dmma<false, true>(h, a, smem) : launch_dmma<false, false>(h, a, smem);
@@ -574,7 +614,7 @@ int wd_cache_clear(wd_handle_t h)
 int wd_set_variant(wd_handle_t h, int variant)
 {
     if (!h) return fail(WD_ERR_ASSERT, "null handle");
-    if (variant < 0 || variant > 3) return fail(WD_ERR_ASSERT, "variant must be 0..3");
+    if (variant < 0 || variant > 4) return fail(WD_ERR_ASSERT, "variant must be 0..4");
     h->variant = variant;
     return WD_OK;
 }

@@ -554,6 +554,362 @@ __global__ void __launch_bounds__(k2_threads(CPLX), 1) k2_dmma_kernel(K2Args a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Real d, second-generation kernel (k2_real_kernel).  Same main loop; what changed around it:
+//   * one staged tile feeds TWO mirror targets.  The butterfly sum S = P0 + P1 belongs to (i,i') and (ir,i'r), the
+//     difference D = P0 - P1 to (ir,i') and (i,i'r): the compute warp stages S and D once each (half the STS of the
+//     first-generation epilogue) and the store warp writes every staged value to an ascending and a descending
+//     target (one LDS, two STG: half the LDS of the old drain);
+//   * tiles are half as large (8 angles) and ride a 2-slot ring per compute warp: staging of tile t+1 overlaps
+//     the drain of tile t, the compute warp is back in its main loop sooner;
+//   * the NEXT chunk's trig tables are generated into a second buffer while the current chunk is computed (each
+//     compute warp does its share after its first unit, while its partner warp keeps the DMMA pipe busy); the
+//     per-chunk CTA barrier and the all-warps trig phase are gone (mbarriers trig_ready / trig_free instead);
+//   * the last, partial wave of chunks is split over several CTAs each (K2Args::tsplit).
+// ------------------------------------------------------------------------------------------------
+constexpr int K2_TILE_ASC = 1, K2_TILE_DESC = 2, K2_TILE_END_ALL = 8;
+constexpr int K2_HT_ROWS = 8;                              // angles per staged half tile
+constexpr int K2_HT_SIZE = K2_HT_ROWS * K2_STG_LD;         // doubles per ring slot
+
+struct K2Tile {                 // descriptor of one staged half tile: 8 angles (one MMA row tile) x <= 64 quadrant rows
+    unsigned long long ea;      // ascending target : element index of (first angle, position 0); position s lives at ea + s
+    unsigned long long ed;      // descending target: position s lives at ed - s
+    int s_hi;                   // valid positions: s < s_hi (quadrant row < Q)
+    int s_lo_d;                 // descending target only: s >= s_lo_d (quadrant row >= zskip)
+    int nrows;                  // existing angles of the tile (1..8); angle ar of the tile is matrix 2*ar further on
+    int dib_a, dib_d;           // (row - col) mod 4 of position 0 in the two targets: sigma(dib_a + s), sigma(dib_d - s)
+    int kind;                   // K2_TILE_ASC | K2_TILE_DESC, or an END marker
+};
+static_assert(sizeof(K2Tile) == 40, "K2Tile layout");
+
+struct K2RSmem {                // offsets in doubles, computed identically on host and device
+    int uq, mu, w, trig, stg, desc, bars, total;
+    int ldt, qpad, trig_size;
+};
+constexpr int K2R_NBARS = 4 * K2_CWARPS + 6;   // full[8][2], empty[8][2], trig_ready[2], trig_free[2], UQ load, counters[2]
+__host__ __device__ inline K2RSmem k2r_smem_layout(int Q, int Kp, int ldu)
+{
+    K2RSmem s;
+    s.ldt = Kp | 4;
+    s.qpad = (Q + 15) & ~15;
+    s.trig_size = 2 * K2_ANG * s.ldt;                     // Tc[16][ldt] then Ts[16][ldt]
+    int o = 0;
+    s.uq = o;   o += s.qpad * ldu;
+    s.mu = o;   o += Kp;
+    s.w = o;    o += Kp;
+    s.trig = o; o += 2 * s.trig_size;                     // two buffers: this chunk's tables and the next one's
+    o = (o + 1) & ~1;
+    s.stg = o;  o += K2_CWARPS * 2 * K2_HT_SIZE;
+    s.desc = o; o += K2_CWARPS * 2 * (int)(sizeof(K2Tile) / 8);
+    s.bars = o; o += K2R_NBARS;
+    s.total = o;
+    return s;
+}
+
+struct K2Item { long long b0; int u_begin, u_end; };
+// work item -> (chunk of 16 angles, range of its units).  Items [0, nfull) are whole chunks; the remaining chunks are
+// split tsplit ways each, so that the last wave (or a batch smaller than the GPU) still occupies every SM.
+__device__ __forceinline__ K2Item k2_item(const K2Args &a, const long long it, const int nunits)
+{
+    K2Item o;
+    if (it < a.nfull) { o.b0 = it * K2_ANG; o.u_begin = 0; o.u_end = nunits; return o; }
+    const long long rr = it - a.nfull;
+    const long long ch = a.nfull + rr / a.tsplit;
+    const int split = (int)(rr - (rr / a.tsplit) * a.tsplit);
+    o.b0 = ch * K2_ANG;
+    o.u_begin = (int)((long long)nunits * split / a.tsplit);
+    o.u_end = (int)((long long)nunits * (split + 1) / a.tsplit);
+    return o;
+}
+
+// trig tables of one chunk: Tc/Ts[row(angle)][kp] = w cos|sin(mu beta), fl(mu*beta) then sincos like src/WignerD.jl:199
+__device__ __forceinline__ void k2_trig_fill(const K2Args &a, const double *sMu, const double *sW, double *tc, const int ldt,
+                                             const int Kp, const long long b0, const int t0, const int nt)
+{
+    double *ts = tc + K2_ANG * ldt;
+#pragma unroll 1
+    for (int idx = t0; idx < K2_ANG * Kp; idx += nt) {
+        const int ang = idx / Kp, kp = idx - ang * Kp;
+        long long b = b0 + ang; if (b >= a.nb) b = a.nb - 1;
+        double sn, cs;
+        sincos(sMu[kp] * a.beta[b], &sn, &cs);
+        const double w = sW[kp];
+        const int row = k2_trig_row(ang);
+        tc[row * ldt + kp] = w * cs;
+        ts[row * ldt + kp] = w * sn;
+    }
+}
+
+struct K2RCtx {                 // what a compute warp needs for its hand-offs
+    double *stg;                // 2 ring slots
+    K2Tile *desc;               // 2 descriptors
+    unsigned long long *full, *empty;   // 2 + 2 mbarriers
+    unsigned tiles;             // tiles handed over so far
+};
+
+// Stage one butterfly result (S or D) of a unit, one angle tile at a time, and hand it to the store warp.
+template <int GMAX>
+__device__ __forceinline__ void k2_emit(const K2Args &a, const K2Ctx &cx, K2RCtx &rc, const double (&val)[2][GMAX][2][2],
+                                        const bool isD, const int qn, const int qbase, const int gcnt)
+{
+    const int N = cx.N, i0 = cx.i0, lane = cx.lane;
+    const int ip = i0 + qn, ipr = N - 1 - ip;
+    const int col_a = isD ? ipr : ip, col_d = isD ? ip : ipr;       // S: (i,i') up, (ir,i'r) down;  D: (i,i'r) up, (ir,i') down
+    const bool both = qn >= cx.zskip;                               // n = 0 mirrors onto itself
+    const int kind = isD ? (K2_TILE_DESC | (both ? K2_TILE_ASC : 0)) : (K2_TILE_ASC | (both ? K2_TILE_DESC : 0));
+    const int row_a = i0 + qbase, row_d = N - 1 - i0 - qbase;
+    const size_t NN = (size_t)N * N;
+#pragma unroll
+    for (int ai = 0; ai < 2; ++ai) {
+        const long long bf = cx.b0 + ai;                            // first angle of the tile
+        if (bf >= a.nb) break;                                      // warp-uniform
+        const unsigned t = rc.tiles;
+        const int slot = t & 1;
+        mbar_wait(rc.empty + slot, ((t >> 1) & 1) ^ 1);             // the store warp has drained tile t - 2
+        if (lane == 0) {
+            K2Tile d;
+            size_t ea = (size_t)bf * NN + (size_t)col_a * N + row_a, ed = (size_t)bf * NN + (size_t)col_d * N + row_d;
+            if (a.wrap > 1) { ea %= a.wrap; ed = ed % a.wrap + 64; } // experiment knob: all output into an L2-sized window
+            d.ea = ea; d.ed = ed;
+            d.s_hi = min(16 * gcnt, cx.Q - qbase);
+            d.s_lo_d = max(0, cx.zskip - qbase);
+            d.nrows = (int)min(8LL, (a.nb - bf + 1) / 2);
+            d.dib_a = (row_a - col_a) & 3; d.dib_d = (row_d - col_d) & 3;
+            d.kind = a.wrap == 1 ? 0 : kind;                         // experiment knob: drain without the store instructions
+            rc.desc[slot] = d;
+        }
+        // the lane owns rows 16g+4c .. 16g+4c+3 of the unit: (even tile, odd tile) interleaved
+        double *p = rc.stg + slot * K2_HT_SIZE + cx.r * K2_STG_LD + 4 * cx.c;
+#pragma unroll
+        for (int g = 0; g < GMAX; ++g) {
+            if (g < gcnt) {
+                reinterpret_cast<double2 *>(p + 16 * g)[0] = make_double2(val[ai][g][0][0], val[ai][g][1][0]);
+                reinterpret_cast<double2 *>(p + 16 * g)[1] = make_double2(val[ai][g][0][1], val[ai][g][1][1]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(rc.full + slot);                 // release: tile + descriptor are visible
+        rc.tiles = t + 1;
+    }
+}
+
+__device__ __forceinline__ void k2_send_marker(const K2Ctx &cx, K2RCtx &rc, const int kind)
+{
+    const unsigned t = rc.tiles;
+    const int slot = t & 1;
+    mbar_wait(rc.empty + slot, ((t >> 1) & 1) ^ 1);
+    if (cx.lane == 0) {
+        K2Tile d;
+        d.ea = d.ed = 0; d.s_hi = d.s_lo_d = d.nrows = d.dib_a = d.dib_d = 0; d.kind = kind;
+        rc.desc[slot] = d;
+    }
+    __syncwarp();
+    if (cx.lane == 0) mbar_arrive(rc.full + slot);
+    rc.tiles = t + 1;
+}
+
+// Store warp: one staged value -> its ascending and its descending target; 256 contiguous bytes per store instruction.
+// The matrix-to-matrix pointer walk is kept as an explicit chain (the asm fences): left alone the compiler hoists the
+// eight multiples of N*N for both targets out of the tile loop and spills them (the store warps own 48 registers).
+__device__ __forceinline__ void k2_drain_pair(const double *buf, double *out, const K2Tile &d, const size_t NN, const int lane)
+{
+    const size_t step = 2 * NN;                                       // angle ar of the tile is matrix 2*ar further on
+#pragma unroll 1
+    for (int s = lane; s < d.s_hi; s += 32) {
+        const double *sp = buf + s;
+        const bool on_a = (d.kind & K2_TILE_ASC) != 0, on_d = (d.kind & K2_TILE_DESC) != 0 && s >= d.s_lo_d;
+        double *pa = out + d.ea + s, *pd = out + d.ed - s;
+        const unsigned sa = sigma_bit(d.dib_a + s), sd = sigma_bit(d.dib_d - s);
+        if (d.nrows == K2_HT_ROWS) {                                  // all 8 loads in flight before the stores
+            double v[K2_HT_ROWS];
+#pragma unroll
+            for (int ar = 0; ar < K2_HT_ROWS; ++ar) v[ar] = sp[ar * K2_STG_LD];
+            if (on_a) {
+#pragma unroll
+                for (int ar = 0; ar < K2_HT_ROWS; ++ar) { *pa = flip(v[ar], sa); pa += step; asm volatile("" : "+l"(pa)); }
+            }
+            if (on_d) {
+#pragma unroll
+                for (int ar = 0; ar < K2_HT_ROWS; ++ar) { *pd = flip(v[ar], sd); pd += step; asm volatile("" : "+l"(pd)); }
+            }
+        } else {
+#pragma unroll 1
+            for (int ar = 0; ar < d.nrows; ++ar) {
+                const double v = sp[ar * K2_STG_LD];
+                if (on_a) *pa = flip(v, sa);
+                if (on_d) *pd = flip(v, sd);
+                pa += step; pd += step;
+            }
+        }
+    }
+}
+
+template <bool HALF>
+__device__ __forceinline__ void k2_unit_real(const K2Args &a, const K2Ctx &cx, K2RCtx &rc, const int qn, const int g0, const int gcnt)
+{
+    constexpr int GMAX = HALF ? 2 : 4;
+    constexpr int NALT = HALF ? 2 : 1;
+    double acc[2][2][GMAX][2][NALT][2];
+#pragma unroll
+    for (int i = 0; i < 2 * 2 * GMAX * 2 * NALT * 2; ++i) (&acc[0][0][0][0][0][0])[i] = 0.0;
+    if (HALF) {
+        if (gcnt == 2) k2_mainloop<HALF, GMAX, (GMAX >= 2 ? 2 : 1)>(acc, cx, qn, g0);
+        else k2_mainloop<HALF, GMAX, 1>(acc, cx, qn, g0);
+    } else {
+        switch (gcnt) {
+        case 4: k2_mainloop<HALF, GMAX, (GMAX >= 4 ? 4 : 1)>(acc, cx, qn, g0); break;
+        case 3: k2_mainloop<HALF, GMAX, (GMAX >= 4 ? 3 : 1)>(acc, cx, qn, g0); break;
+        case 2: k2_mainloop<HALF, GMAX, (GMAX >= 2 ? 2 : 1)>(acc, cx, qn, g0); break;
+        default: k2_mainloop<HALF, GMAX, 1>(acc, cx, qn, g0); break;
+        }
+    }
+    // butterfly: S = P0 + P1, D = P0 - P1 (half-integer j: D from the accumulators of the other trig function)
+    double vs[2][GMAX][2][2], vd[2][GMAX][2][2];
+#pragma unroll
+    for (int ai = 0; ai < 2; ++ai)
+#pragma unroll
+        for (int g = 0; g < GMAX; ++g)
+#pragma unroll
+            for (int eo = 0; eo < 2; ++eo)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    vs[ai][g][eo][h] = acc[0][ai][g][eo][0][h] + acc[1][ai][g][eo][0][h];
+                    vd[ai][g][eo][h] = acc[0][ai][g][eo][NALT - 1][h] - acc[1][ai][g][eo][NALT - 1][h];
+                }
+    k2_emit<GMAX>(a, cx, rc, vs, false, qn, 16 * g0, gcnt);
+    k2_emit<GMAX>(a, cx, rc, vd, true, qn, 16 * g0, gcnt);
+}
+
+template <bool HALF>
+__global__ void __launch_bounds__(k2_threads(false), 1) k2_real_kernel(K2Args a)
+{
+    constexpr int GMAX = HALF ? 2 : 4;
+    constexpr int NT = k2_threads(false);
+    constexpr int NC = K2_CWARPS * 32;
+    extern __shared__ __align__(16) double sm[];
+    const PlanDev &p = a.p;
+    const int Q = p.Q, Kp = p.Kp, ldu = p.ldu;
+    const K2RSmem L = k2r_smem_layout(Q, Kp, ldu);
+    const int ldt = L.ldt;
+    double *sUQ = sm + L.uq, *sMu = sm + L.mu, *sW = sm + L.w;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sm + L.bars);
+    unsigned long long *trig_ready = bars + 4 * K2_CWARPS, *trig_free = trig_ready + 2, *uq_bar = trig_free + 2;
+    int *sCounter = reinterpret_cast<int *>(uq_bar + 1);                    // [2]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    const int ngroups = L.qpad >> 4;
+    const int upc = (ngroups + GMAX - 1) / GMAX;          // parts per column
+    const int gbase = ngroups / upc, grem = ngroups - gbase * upc;   // the first grem parts have gbase+1 groups
+    const int nunits = Q * upc;
+    // this CTA's items: blockIdx.x, blockIdx.x + gridDim.x, ...  (the grid never exceeds the item count)
+    const long long nmine = (a.nitems - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+    // one-time: UQ -> shared through the TMA engine (one bulk copy, mbarrier-signalled); zero pad rows, mu, w by hand
+    {
+        const unsigned uq_bytes = (unsigned)(Q * ldu) * 8u;        // a multiple of 16: ldu is even
+        if (tid == 0) {
+            mbar_init(uq_bar, 1);
+            for (int w = 0; w < 4 * K2_CWARPS; ++w) mbar_init(bars + w, 1);
+            for (int b = 0; b < 2; ++b) { mbar_init(trig_ready + b, K2_CWARPS); mbar_init(trig_free + b, K2_CWARPS); }
+            mbar_init_fence();
+            mbar_expect_tx(uq_bar, uq_bytes);
+            bulk_load(sUQ, p.uq, uq_bytes, uq_bar);
+        }
+        for (int i = Q * ldu + tid; i < L.qpad * ldu; i += NT) sUQ[i] = 0.0;
+        for (int i = tid; i < Kp; i += NT) { sMu[i] = p.mu[i]; sW[i] = p.w[i]; }
+        __syncthreads();                                           // the mbarriers are initialised for everybody
+        mbar_wait(uq_bar, 0);
+    }
+
+    if (warp >= K2_CWARPS) {
+        // ---- store warp q: drains the ring of compute warp q ----
+        // (no trig work here: a call -- sincos' slow path -- below setmaxnreg.dec crashes ptxas 12.9)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(K2_REGS_STORE));
+        const int q = warp - K2_CWARPS;
+        const double *ring = sm + L.stg + q * (2 * K2_HT_SIZE);
+        const K2Tile *desc = reinterpret_cast<const K2Tile *>(sm + L.desc) + 2 * q;
+        unsigned long long *full = bars + 2 * q, *empty = bars + 2 * K2_CWARPS + 2 * q;
+        const size_t NN = (size_t)p.N * p.N;
+        for (unsigned t = 0;; ++t) {
+            const int slot = t & 1;
+            mbar_wait(full + slot, (t >> 1) & 1);                      // acquire: tile + descriptor are visible
+            const K2Tile d = desc[slot];
+            if (d.kind == K2_TILE_END_ALL) break;
+            k2_drain_pair(ring + slot * K2_HT_SIZE, a.out, d, NN, lane);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + slot);                  // release: the slot may be overwritten
+        }
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(K2_REGS_COMPUTE));
+
+    K2Ctx cx;
+    cx.sUQ = sUQ; cx.sTc = nullptr; cx.sTs = nullptr; cx.sPh = nullptr;
+    cx.stg = nullptr; cx.desc = nullptr; cx.full = nullptr; cx.empty = nullptr;
+    cx.ldu = ldu; cx.ldt = ldt; cx.N = p.N; cx.Q = Q; cx.i0 = p.N - Q; cx.zskip = p.zskip;
+    cx.Kp = Kp; cx.K0p = p.K0p; cx.twoj = p.twoj;
+    cx.lane = lane; cx.r = lane >> 2; cx.c = lane & 3;
+    cx.tiles = 0;
+    K2RCtx rc;
+    rc.stg = sm + L.stg + warp * (2 * K2_HT_SIZE);
+    rc.desc = reinterpret_cast<K2Tile *>(sm + L.desc) + 2 * warp;
+    rc.full = bars + 2 * warp; rc.empty = bars + 2 * K2_CWARPS + 2 * warp;
+    rc.tiles = 0;
+    // hand-off between the two compute warps (w, w+4) of an SM sub-partition: see k2_dmma_kernel
+    cx.krel = a.handoff - 1;
+    cx.bar_me = a.handoff ? 2 + warp : 0;
+    cx.bar_other = a.handoff ? 2 + (warp ^ 4) : 0;
+    if (a.handoff && (warp & 4)) named_bar_arrive(cx.bar_other, 64);       // warps 0..3 take the first turn
+
+    // The trig tables and the unit counter of item k+1 are made DURING item k, into the other buffer: every compute
+    // warp contributes its share right after its first unit of item k -- its partner warp is then in its main loop,
+    // so the DMMA pipe stays busy (the first-generation kernel stopped all warps at a CTA barrier for this).
+    //   trig_ready[b]: 8 arrivals (one per compute warp) = the tables in buffer b are complete;
+    //   trig_free[b] : 8 arrivals = every compute warp has finished the item that used buffer b.
+    auto prefetch = [&](const long long kn) {
+        const int bn = (int)(kn & 1);
+        if (kn >= 2) mbar_wait(trig_free + bn, (unsigned)((kn - 2) >> 1) & 1u);      // item kn-2 has left this buffer
+        const K2Item itn = k2_item(a, blockIdx.x + kn * gridDim.x, nunits);
+        k2_trig_fill(a, sMu, sW, sm + L.trig + bn * L.trig_size, ldt, Kp, itn.b0, tid, NC);
+        if (tid == 0) sCounter[bn] = itn.u_begin;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(trig_ready + bn);
+    };
+    // (every sincos call site sits below setmaxnreg.inc: ptxas 12.9 crashes when the slow-path callee is reachable from
+    // regions with different register budgets)
+    prefetch(0);
+#pragma unroll 1
+    for (long long k = 0; k < nmine; ++k) {
+        const int b = (int)(k & 1);
+        const K2Item it = k2_item(a, blockIdx.x + k * gridDim.x, nunits);
+        mbar_wait(trig_ready + b, (unsigned)(k >> 1) & 1u);           // this item's tables and counter are in place
+        cx.sTc = sm + L.trig + b * L.trig_size; cx.sTs = cx.sTc + K2_ANG * ldt;
+        cx.b0 = it.b0;
+        bool pre = k + 1 >= nmine;                                    // nothing left to prefetch
+        // dynamic unit scheduler (one shared counter per item): unit v -> part v % upc of column v / upc.  The
+        // eight warps then work on adjacent columns, whose output is adjacent in memory.
+#pragma unroll 1
+        for (;;) {
+            if (cx.bar_me) named_bar_sync(cx.bar_me, 64);
+            int v = 0;
+            if (lane == 0) v = atomicAdd(sCounter + b, 1);
+            v = __shfl_sync(0xffffffffu, v, 0);
+            const bool have = v < it.u_end;
+            if (have) {
+                const int qn = v / upc, part = v - qn * upc;
+                const int g0 = part * gbase + min(part, grem);
+                const int gcnt = gbase + (part < grem ? 1 : 0);
+                k2_unit_real<HALF>(a, cx, rc, qn, g0, gcnt);
+            } else if (cx.bar_other) named_bar_arrive(cx.bar_other, 64);      // leaving: pass the token on
+            if (!pre) { prefetch(k + 1); pre = true; }                        // after the first unit (or when there is none)
+            if (!have) break;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(trig_free + b);                    // this warp is done with buffer b and its counter
+    }
+    k2_send_marker(cx, rc, K2_TILE_END_ALL);
+}
+
+// ------------------------------------------------------------------------------------------------
 // FP64 peak micro-benchmarks (roofline calibration)
 // ------------------------------------------------------------------------------------------------
 __global__ void fp64_peak_kernel(int kind, int iters, double *sink)

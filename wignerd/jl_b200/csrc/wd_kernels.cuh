@@ -147,6 +147,8 @@ struct K2Args {
     int handoff;                          // DMMA kernel: midpoint hand-off between paired compute warps
     int nsub;                             // DMMA kernel: 16-angle chunks per barrier phase (1 or 2)
     int nsplit;                           // DMMA kernel: CTAs per chunk (small batches)
+    long long nfull, nitems;              // real-d DMMA kernel: whole-chunk items, all items (k2_item)
+    int tsplit;                           // real-d DMMA kernel: CTAs per chunk of the last partial wave
     unsigned long long wrap;              // experiment knob (WD_K2_WRAP): wrap the output index to an L2-sized window; 0 = off
 };
 
