@@ -278,7 +278,7 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
     a.nb = nb; a.out = out; a.equator = equator ? 1 : 0;
     a.nsplit = 1; a.wrap = 0; a.nfull = 0; a.nitems = 0; a.tsplit = 1;
     {
-        const char *e = getenv("WD_K2_WRAP");            // kernel-experiment knob: output index modulo this many doubles
+        const char *e = getenv("WD_K2_WRAP");            // kernel-experiment knob: 1 = no store instructions (SM-side time)
         if (e) a.wrap = strtoull(e, nullptr, 10);
     }
     {

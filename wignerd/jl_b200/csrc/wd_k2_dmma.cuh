@@ -34,8 +34,8 @@ constexpr int K2_SWARPS = 8;               // store warps, one per compute warp 
 constexpr int K2_ANG = 16;                 // angles per chunk (2 MMA row tiles)
 constexpr int K2_STG_LD = 66;              // staging row stride (doubles): == 2 mod 16 -> conflict-free 16-byte stores
 constexpr int K2_STG_ROWS = 16;            // both angle tiles of a chunk
-constexpr int K2_REGS_COMPUTE = 208;
-constexpr int K2_REGS_STORE = 48;             // 8*32*208 + 8*32*48 = 65536 = the whole register file
+constexpr int K2_REGS_COMPUTE = 200;
+constexpr int K2_REGS_STORE = 56;             // 8*32*200 + 8*32*56 = 65536 = the whole register file
 __host__ __device__ constexpr int k2_threads(bool cplx) { return (K2_CWARPS + (cplx ? 0 : K2_SWARPS)) * 32; }
 
 __device__ __forceinline__ void dmma(double (&d)[2], double a, double b)
@@ -267,8 +267,7 @@ __device__ __forceinline__ void k2_store_target(const K2Args &a, K2Ctx &cx, cons
 #pragma unroll
     for (int t = 0; t < 4; ++t) sb[t] = sigma_bit(DESC ? dib - t : dib + t);
     const size_t NN = (size_t)N * N;
-    size_t e00 = (size_t)cx.b0 * NN + (size_t)col * N + row0;         // angle 0 of the chunk, staging position 0
-    if (a.wrap) e00 %= a.wrap;                                        // experiment knob: SM-side time without DRAM writes
+    const size_t e00 = (size_t)cx.b0 * NN + (size_t)col * N + row0;   // angle 0 of the chunk, staging position 0
     double *buf = cx.stg;
     if constexpr (!CPLX) {
         mbar_wait(cx.empty, (cx.tiles & 1) ^ 1);                     // the store warp has drained the previous tile
@@ -644,37 +643,37 @@ struct K2RCtx {                 // what a compute warp needs for its hand-offs
     K2Tile *desc;               // 2 descriptors
     unsigned long long *full, *empty;   // 2 + 2 mbarriers
     unsigned tiles;             // tiles handed over so far
+    size_t NN, e_item, e_ip, e_ipr;     // N*N; element index of the item's first matrix; of output columns i', i'r in it
+    int ntiles, nrows0, nrows1; // existing angle tiles of the item and their angle counts (ragged last chunk)
 };
 
 // Stage one butterfly result (S or D) of a unit, one angle tile at a time, and hand it to the store warp.
+// rc.e_ip / rc.e_ipr: element index of (angle 0 of the chunk, row 0) of output columns i' and i'r (set once per unit).
 template <int GMAX>
 __device__ __forceinline__ void k2_emit(const K2Args &a, const K2Ctx &cx, K2RCtx &rc, const double (&val)[2][GMAX][2][2],
                                         const bool isD, const int qn, const int qbase, const int gcnt)
 {
-    const int N = cx.N, i0 = cx.i0, lane = cx.lane;
-    const int ip = i0 + qn, ipr = N - 1 - ip;
-    const int col_a = isD ? ipr : ip, col_d = isD ? ip : ipr;       // S: (i,i') up, (ir,i'r) down;  D: (i,i'r) up, (ir,i') down
+    const int lane = cx.lane;
     const bool both = qn >= cx.zskip;                               // n = 0 mirrors onto itself
-    const int kind = isD ? (K2_TILE_DESC | (both ? K2_TILE_ASC : 0)) : (K2_TILE_ASC | (both ? K2_TILE_DESC : 0));
-    const int row_a = i0 + qbase, row_d = N - 1 - i0 - qbase;
-    const size_t NN = (size_t)N * N;
+    const int row_a = cx.i0 + qbase, row_d = cx.N - 1 - cx.i0 - qbase;
+    const int ip = cx.i0 + qn;
 #pragma unroll
     for (int ai = 0; ai < 2; ++ai) {
-        const long long bf = cx.b0 + ai;                            // first angle of the tile
-        if (bf >= a.nb) break;                                      // warp-uniform
+        if (ai >= rc.ntiles) break;                                 // ragged last chunk (warp-uniform)
         const unsigned t = rc.tiles;
         const int slot = t & 1;
         mbar_wait(rc.empty + slot, ((t >> 1) & 1) ^ 1);             // the store warp has drained tile t - 2
         if (lane == 0) {
+            // S: (i,i') upwards, (ir,i'r) downwards;  D: (i,i'r) upwards, (ir,i') downwards
             K2Tile d;
-            size_t ea = (size_t)bf * NN + (size_t)col_a * N + row_a, ed = (size_t)bf * NN + (size_t)col_d * N + row_d;
-            if (a.wrap > 1) { ea %= a.wrap; ed = ed % a.wrap + 64; } // experiment knob: all output into an L2-sized window
-            d.ea = ea; d.ed = ed;
+            d.ea = (isD ? rc.e_ipr : rc.e_ip) + row_a + (ai ? rc.NN : 0);
+            d.ed = (isD ? rc.e_ip : rc.e_ipr) + row_d + (ai ? rc.NN : 0);
             d.s_hi = min(16 * gcnt, cx.Q - qbase);
             d.s_lo_d = max(0, cx.zskip - qbase);
-            d.nrows = (int)min(8LL, (a.nb - bf + 1) / 2);
+            d.nrows = ai ? rc.nrows1 : rc.nrows0;
+            const int col_a = isD ? cx.N - 1 - ip : ip, col_d = isD ? ip : cx.N - 1 - ip;
             d.dib_a = (row_a - col_a) & 3; d.dib_d = (row_d - col_d) & 3;
-            d.kind = a.wrap == 1 ? 0 : kind;                         // experiment knob: drain without the store instructions
+            d.kind = a.wrap == 1 ? 0 : (isD ? (K2_TILE_DESC | (both ? K2_TILE_ASC : 0)) : (K2_TILE_ASC | (both ? K2_TILE_DESC : 0)));
             rc.desc[slot] = d;
         }
         // the lane owns rows 16g+4c .. 16g+4c+3 of the unit: (even tile, odd tile) interleaved
@@ -708,8 +707,9 @@ __device__ __forceinline__ void k2_send_marker(const K2Ctx &cx, K2RCtx &rc, cons
 }
 
 // Store warp: one staged value -> its ascending and its descending target; 256 contiguous bytes per store instruction.
-// The matrix-to-matrix pointer walk is kept as an explicit chain (the asm fences): left alone the compiler hoists the
-// eight multiples of N*N for both targets out of the tile loop and spills them (the store warps own 48 registers).
+// All eight matrix pointers of a target are formed BEFORE its stores issue: a pointer that is advanced in place right
+// after its store waits for the store to read it (write-after-read through the LSU queue, ~25 cycles per store in
+// the ncu source view; the store warps were busy 83 % of the time and the compute warps waited for free slots).
 __device__ __forceinline__ void k2_drain_pair(const double *buf, double *out, const K2Tile &d, const size_t NN, const int lane)
 {
     const size_t step = 2 * NN;                                       // angle ar of the tile is matrix 2*ar further on
@@ -721,15 +721,20 @@ __device__ __forceinline__ void k2_drain_pair(const double *buf, double *out, co
         const unsigned sa = sigma_bit(d.dib_a + s), sd = sigma_bit(d.dib_d - s);
         if (d.nrows == K2_HT_ROWS) {                                  // all 8 loads in flight before the stores
             double v[K2_HT_ROWS];
+            double *q[K2_HT_ROWS];
 #pragma unroll
             for (int ar = 0; ar < K2_HT_ROWS; ++ar) v[ar] = sp[ar * K2_STG_LD];
             if (on_a) {
 #pragma unroll
-                for (int ar = 0; ar < K2_HT_ROWS; ++ar) { *pa = flip(v[ar], sa); pa += step; asm volatile("" : "+l"(pa)); }
+                for (int ar = 0; ar < K2_HT_ROWS; ++ar) q[ar] = pa + ar * step;
+#pragma unroll
+                for (int ar = 0; ar < K2_HT_ROWS; ++ar) *q[ar] = flip(v[ar], sa);
             }
             if (on_d) {
 #pragma unroll
-                for (int ar = 0; ar < K2_HT_ROWS; ++ar) { *pd = flip(v[ar], sd); pd += step; asm volatile("" : "+l"(pd)); }
+                for (int ar = 0; ar < K2_HT_ROWS; ++ar) q[ar] = pd + ar * step;
+#pragma unroll
+                for (int ar = 0; ar < K2_HT_ROWS; ++ar) *q[ar] = flip(v[ar], sd);
             }
         } else {
 #pragma unroll 1
@@ -775,6 +780,8 @@ __device__ __forceinline__ void k2_unit_real(const K2Args &a, const K2Ctx &cx, K
                     vs[ai][g][eo][h] = acc[0][ai][g][eo][0][h] + acc[1][ai][g][eo][0][h];
                     vd[ai][g][eo][h] = acc[0][ai][g][eo][NALT - 1][h] - acc[1][ai][g][eo][NALT - 1][h];
                 }
+    rc.e_ip = rc.e_item + (size_t)(cx.i0 + qn) * cx.N;
+    rc.e_ipr = rc.e_item + (size_t)(cx.N - 1 - cx.i0 - qn) * cx.N;
     k2_emit<GMAX>(a, cx, rc, vs, false, qn, 16 * g0, gcnt);
     k2_emit<GMAX>(a, cx, rc, vd, true, qn, 16 * g0, gcnt);
 }
@@ -854,6 +861,7 @@ __global__ void __launch_bounds__(k2_threads(false), 1) k2_real_kernel(K2Args a)
     rc.desc = reinterpret_cast<K2Tile *>(sm + L.desc) + 2 * warp;
     rc.full = bars + 2 * warp; rc.empty = bars + 2 * K2_CWARPS + 2 * warp;
     rc.tiles = 0;
+    rc.NN = (size_t)p.N * p.N;
     // hand-off between the two compute warps (w, w+4) of an SM sub-partition: see k2_dmma_kernel
     cx.krel = a.handoff - 1;
     cx.bar_me = a.handoff ? 2 + warp : 0;
@@ -884,6 +892,10 @@ __global__ void __launch_bounds__(k2_threads(false), 1) k2_real_kernel(K2Args a)
         mbar_wait(trig_ready + b, (unsigned)(k >> 1) & 1u);           // this item's tables and counter are in place
         cx.sTc = sm + L.trig + b * L.trig_size; cx.sTs = cx.sTc + K2_ANG * ldt;
         cx.b0 = it.b0;
+        rc.e_item = (size_t)it.b0 * rc.NN;
+        rc.nrows0 = (int)min(8LL, (a.nb - it.b0 + 1) / 2);
+        rc.nrows1 = (int)min(8LL, (a.nb - it.b0) / 2);
+        rc.ntiles = rc.nrows1 > 0 ? 2 : 1;
         bool pre = k + 1 >= nmine;                                    // nothing left to prefetch
         // dynamic unit scheduler (one shared counter per item): unit v -> part v % upc of column v / upc.  The
         // eight warps then work on adjacent columns, whose output is adjacent in memory.

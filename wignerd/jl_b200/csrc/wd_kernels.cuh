@@ -149,7 +149,7 @@ struct K2Args {
     int nsplit;                           // DMMA kernel: CTAs per chunk (small batches)
     long long nfull, nitems;              // real-d DMMA kernel: whole-chunk items, all items (k2_item)
     int tsplit;                           // real-d DMMA kernel: CTAs per chunk of the last partial wave
-    unsigned long long wrap;              // experiment knob (WD_K2_WRAP): wrap the output index to an L2-sized window; 0 = off
+    unsigned long long wrap;              // experiment knob (WD_K2_WRAP=1): run the real-d DMMA kernel without its store instructions
 };
 
 template <bool CPLX>
