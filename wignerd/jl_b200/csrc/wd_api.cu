@@ -65,7 +65,7 @@ struct wd_handle_s {
     int table_max = -1;
     bool table_dirty = true;
     int *d_flag = nullptr;           // error flag / scratch ints
-    bool attr_set[2][2] = {{false, false}, {false, false}};
+    bool attr_set_cplx[2] = {false, false};
     bool attr_set_stream[2] = {false, false};
     bool attr_set_real[2] = {false, false};
     // host-path workspace, kept across calls (grow-only): angle vectors and two output slabs + their events
@@ -168,37 +168,33 @@ int get_plan(wd_handle_t h, int twoj, const Plan **out)
     return WD_OK;
 }
 
-bool dmma_fits(wd_handle_t h, const PlanDev &p, bool cplx, size_t *bytes, int *nsub, int nsub_max)
+// Resident DMMA kernel for complex D (k2_cplx_kernel)
+bool cplx_fits(wd_handle_t h, const PlanDev &p, size_t *bytes)
 {
-    for (int ns = cplx ? 1 : nsub_max; ns >= 1; --ns) {
-        const K2Smem L = k2_smem_layout(p.Q, p.Kp, p.ldu, cplx, ns);
-        *bytes = (size_t)L.total * sizeof(double);
-        *nsub = ns;
-        if (*bytes <= h->smem_optin) return true;
-    }
-    return false;
+    const K2Smem L = k2_smem_layout(p.Q, p.Kp, p.ldu);
+    *bytes = (size_t)L.total * sizeof(double);
+    return *bytes <= h->smem_optin;
 }
 
-template <bool HALF, bool CPLX>
-int launch_dmma(wd_handle_t h, const K2Args &a, size_t smem)
+template <bool HALF>
+int launch_cplx(wd_handle_t h, const K2Args &a, size_t smem)
 {
-    if (!h->attr_set[HALF][CPLX]) {
-        CU(cudaFuncSetAttribute(k2_dmma_kernel<HALF, CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)h->smem_optin));
-        h->attr_set[HALF][CPLX] = true;
+    if (!h->attr_set_cplx[HALF]) {
+        CU(cudaFuncSetAttribute(k2_cplx_kernel<HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+        h->attr_set_cplx[HALF] = true;
     }
-    const long long nchunks = (a.nb + K2_ANG * a.nsub - 1) / (K2_ANG * a.nsub);
+    const long long nchunks = (a.nb + K2_ANG - 1) / K2_ANG;
     // fewer chunks than SMs: split every chunk's units over several CTAs (each rebuilds the chunk's small trig tables)
     K2Args b = a;
     b.nsplit = nchunks >= h->num_sms ? 1 : (int)std::min<long long>(16, (h->num_sms + nchunks - 1) / nchunks);
     const int grid = (int)std::min<long long>(nchunks * b.nsplit, h->num_sms);
-    k2_dmma_kernel<HALF, CPLX><<<grid, k2_threads(CPLX), smem, h->stream>>>(b);
+    k2_cplx_kernel<HALF><<<grid, K2_THREADS_CPLX, smem, h->stream>>>(b);
     h->launches++;
     CU(cudaGetLastError());
     return WD_OK;
 }
 
-// Resident DMMA kernel for real d (second generation: k2_real_kernel)
+// Resident DMMA kernel for real d (k2_real_kernel)
 bool real_fits(wd_handle_t h, const PlanDev &p, size_t *bytes)
 {
     const K2RSmem L = k2r_smem_layout(p.Q, p.Kp, p.ldu);
@@ -227,7 +223,7 @@ int launch_real(wd_handle_t h, const K2Args &a, size_t smem)
     }
     b.nitems = b.nfull + rem * b.tsplit;
     const int grid = (int)std::min<long long>(b.nitems, G);
-    k2_real_kernel<HALF><<<grid, k2_threads(false), smem, h->stream>>>(b);
+    k2_real_kernel<HALF><<<grid, K2_THREADS_REAL, smem, h->stream>>>(b);
     h->launches++;
     CU(cudaGetLastError());
     return WD_OK;
@@ -259,7 +255,7 @@ int launch_stream(wd_handle_t h, const K2Args &a)
     const int ngroups = (a.p.Q + 15) / 16;
     const long long ntiles = nac * ((ngroups + gmax - 1) / gmax) * ((a.p.Q + K2_CWARPS - 1) / K2_CWARPS);
     const int grid = (int)std::min<long long>(ntiles, h->num_sms);
-    k2_stream_kernel<HALF><<<grid, k2_threads(false), smem, h->stream>>>(sa);
+    k2_stream_kernel<HALF><<<grid, K2_THREADS_REAL, smem, h->stream>>>(sa);
     h->launches += 2;
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(trig, h->stream);
@@ -282,39 +278,26 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
         if (e) a.wrap = strtoull(e, nullptr, 10);
     }
     {
-        // hand-off between the two compute warps of a sub-partition: the partner is released when ~80 % of the k-steps
-        // of a main loop are done (measured at cfg-2: release at 50 % 10.7 ms, 80 % 10.1 ms, 100 % 11.0 ms, off 11.4 ms).
+        // hand-off between the two compute warps of a sub-partition: the partner is released when ~2/3 of the k-steps of a
+        // main loop are done (real d, second-generation kernel, cfg-2: release at 50 % 9.43 ms, 58-73 % 9.21-9.24 ms, 81 %
+        // 9.31 ms, 96 % 10.1 ms, off 10.6 ms; complex D, whose warps also drain their tiles: 80 %).
         // Encoding: 0 = off; h = release after h-1 pairs of k-steps of class 0, or (h-1 >= 100) h-101 pairs of class 1.
         const int s0 = pl.dev.K0p / 4, s1 = pl.dev.K1p / 4;
-        const int target = (4 * (s0 + s1) + 4) / 5;
+        const int target = cplx ? (4 * (s0 + s1) + 4) / 5 : (2 * (s0 + s1) + 1) / 3;
         a.handoff = 1 + (target <= s0 ? target / 2 : 100 + (target - s0) / 2);
         const char *e = getenv("WD_K2_HANDOFF");        // kernel-experiment knob
         if (e) a.handoff = atoi(e);
     }
-    // two 16-angle chunks per barrier phase measured no gain (10.98 vs 11.25 ms at cfg-2): one chunk unless asked for
-    int nsub_max = 1;
-    {
-        const char *e = getenv("WD_K2_NSUB");            // kernel-experiment knob
-        if (e && atoi(e) == 2) nsub_max = 2;
-    }
-    int nsub = 1;
     size_t smem = 0;
-    bool fits = dmma_fits(h, pl.dev, cplx, &smem, &nsub, nsub_max);
-    a.nsub = nsub;
-    // real d: the second-generation kernel (variant 4 = the first-generation one, kept for A/B measurements)
-    const bool gen2 = !cplx && h->variant != 4;
-    if (gen2) fits = real_fits(h, pl.dev, &smem);
-    int variant = h->variant == 4 ? 2 : h->variant;
+    const bool fits = cplx ? cplx_fits(h, pl.dev, &smem) : real_fits(h, pl.dev, &smem);
+    const int variant = h->variant;
     if (variant == 2 && !fits) return fail(WD_ERR_UNSUPPORTED, "2j = %d does not fit the DMMA kernel (%zu B of shared memory)", pl.dev.twoj, smem);
     // Equator() requests (single matrices, exact zeros of :230-237) take the plain kernel
     if (variant == 3 && !cplx && !equator) return (pl.dev.twoj & 1) ? launch_stream<true>(h, a) : launch_stream<false>(h, a);
     const bool use_dmma = !equator && ((variant == 2) || (variant == 0 && fits));
     const bool half = pl.dev.twoj & 1;
-    if (use_dmma && gen2) return half ? launch_real<true>(h, a, smem) : launch_real<false>(h, a, smem);
-    if (use_dmma) {
-        if (half) return cplx ? launch_dmma<true, true>(h, a, smem) : launch_dmma<true, false>(h, a, smem);
-        return cplx ? launch_dmma<false, true>(h, a, smem) : launch_dmma<false, false>(h, a, smem);
-    }
+    if (use_dmma && !cplx) return half ? launch_real<true>(h, a, smem) : launch_real<false>(h, a, smem);
+    if (use_dmma) return half ? launch_cplx<true>(h, a, smem) : launch_cplx<false>(h, a, smem);
     // real d for a table that does not fit in shared memory: the streaming DMMA kernel
     if (!cplx && !equator && variant != 1) return half ? launch_stream<true>(h, a) : launch_stream<false>(h, a);
     const size_t psm = 2 * (size_t)pl.dev.Kp * sizeof(double);
@@ -614,7 +597,7 @@ int wd_cache_clear(wd_handle_t h)
 int wd_set_variant(wd_handle_t h, int variant)
 {
     if (!h) return fail(WD_ERR_ASSERT, "null handle");
-    if (variant < 0 || variant > 4) return fail(WD_ERR_ASSERT, "variant must be 0..4");
+    if (variant < 0 || variant > 3) return fail(WD_ERR_ASSERT, "variant must be 0..3");
     h->variant = variant;
     return WD_OK;
 }

@@ -33,10 +33,12 @@ constexpr int K2_CWARPS = 8;               // compute warps
 constexpr int K2_SWARPS = 8;               // store warps, one per compute warp (real-d kernels only)
 constexpr int K2_ANG = 16;                 // angles per chunk (2 MMA row tiles)
 constexpr int K2_STG_LD = 66;              // staging row stride (doubles): == 2 mod 16 -> conflict-free 16-byte stores
-constexpr int K2_STG_ROWS = 16;            // both angle tiles of a chunk
+constexpr int K2_HT_ROWS = 8;               // angles per staged tile (one MMA row tile = "half tile" of a chunk)
+constexpr int K2_HT_SIZE = K2_HT_ROWS * K2_STG_LD;   // doubles per staged tile
 constexpr int K2_REGS_COMPUTE = 200;
 constexpr int K2_REGS_STORE = 56;             // 8*32*200 + 8*32*56 = 65536 = the whole register file
-__host__ __device__ constexpr int k2_threads(bool cplx) { return (K2_CWARPS + (cplx ? 0 : K2_SWARPS)) * 32; }
+constexpr int K2_THREADS_REAL = (K2_CWARPS + K2_SWARPS) * 32;      // real-d kernels: compute + store warps
+constexpr int K2_THREADS_CPLX = K2_CWARPS * 32;                    // complex-D kernel: every warp does both jobs
 
 __device__ __forceinline__ void dmma(double (&d)[2], double a, double b)
 {
@@ -98,20 +100,11 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads)
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// what a store warp needs to know about a staged tile
-struct K2Desc {
-    unsigned long long e00;     // element index of (angle 0 of the chunk, staging position 0)
-    int s_lo, s_hi;             // valid staging positions; s_hi < 0: the compute warp has finished
-    int nrows0, nrows1;         // existing angles of tile 0 (even angles) / tile 1 (odd angles)
-    int dib;                    // row - col of staging position 0 (mod 4): the store warp applies sigma(dib + s)
-    int pad;
+struct K2Smem {                 // complex-D kernel; offsets in doubles, computed identically on host and device
+    int uq, mu, w, tc, ts, ph, stg, bars, total;
+    int ldt, qpad;
 };
-
-struct K2Smem {                 // offsets in doubles, computed identically on host and device
-    int uq, mu, w, tc, ts, ph, stg, desc, bars, total;
-    int ldt, qpad, stg_rows;
-};
-__host__ __device__ inline K2Smem k2_smem_layout(int Q, int Kp, int ldu, bool cplx, int nsub = 1)
+__host__ __device__ inline K2Smem k2_smem_layout(int Q, int Kp, int ldu)
 {
     K2Smem s;
     s.ldt = Kp | 4;                        // == 4 mod 8: conflict-free for 8 consecutive rows x 4 cols
@@ -120,26 +113,21 @@ __host__ __device__ inline K2Smem k2_smem_layout(int Q, int Kp, int ldu, bool cp
     s.uq = o;  o += s.qpad * ldu;
     s.mu = o;  o += Kp;
     s.w = o;   o += Kp;
-    s.tc = o;  o += nsub * K2_ANG * s.ldt;             // nsub chunks of 16 angles share one barrier phase
-    s.ts = o;  o += nsub * K2_ANG * s.ldt;
-    s.ph = o;  o += cplx ? 4 * K2_ANG * Q : 0;          // cos(m a), sin(m a), cos(n g), sin(n g)  [16][Q]
+    s.tc = o;  o += K2_ANG * s.ldt;
+    s.ts = o;  o += K2_ANG * s.ldt;
+    s.ph = o;  o += 4 * K2_ANG * Q;                     // cos(m a), sin(m a), cos(n g), sin(n g)  [16][Q]
     o = (o + 1) & ~1;
-    s.stg_rows = cplx ? 8 : K2_STG_ROWS;       // complex D stages one angle tile at a time (room for the phase tables)
-    s.stg = o;  o += K2_CWARPS * s.stg_rows * K2_STG_LD;
-    s.desc = o; o += K2_CWARPS * (int)(sizeof(K2Desc) / 8);
-    s.bars = o; o += 2 * K2_CWARPS + 2;                 // full[8], empty[8], UQ-load barrier, unit counter
+    s.stg = o;  o += K2_CWARPS * K2_HT_ROWS * K2_STG_LD;   // one angle tile (8 angles) per compute warp
+    s.bars = o; o += 2;                                 // UQ-load barrier, unit counter
     s.total = o;
     return s;
 }
 
 struct K2Ctx {                  // per-thread constants of a compute warp
     const double *sUQ, *sTc, *sTs, *sPh;
-    double *stg;
-    K2Desc *desc;
-    void *full, *empty;
+    double *stg;                // complex-D kernel: the warp's staging tile
     int ldu, ldt, N, Q, i0, zskip, Kp, K0p, twoj;
     int lane, r, c;
-    unsigned tiles;             // tiles handed to the store warp so far (mbarrier phase)
     int bar_me, bar_other;      // named barriers of the hand-off between the two warps of a sub-partition (0 = off)
     int krel;                   // release point: after this many pairs of k-steps of the first class
     long long b0;
@@ -147,6 +135,24 @@ struct K2Ctx {                  // per-thread constants of a compute warp
 
 // row of the trig tables that holds angle a of the chunk: even angles first (tile 0), odd angles second (tile 1)
 __device__ __forceinline__ int k2_trig_row(int a) { return ((a & 1) << 3) + (a >> 1); }
+
+// trig tables of one chunk: Tc/Ts[row(angle)][kp] = w cos|sin(mu beta), fl(mu*beta) then sincos like src/WignerD.jl:199
+__device__ __forceinline__ void k2_trig_fill(const K2Args &a, const double *sMu, const double *sW, double *tc, const int ldt,
+                                             const int Kp, const long long b0, const int t0, const int nt)
+{
+    double *ts = tc + K2_ANG * ldt;
+#pragma unroll 1
+    for (int idx = t0; idx < K2_ANG * Kp; idx += nt) {
+        const int ang = idx / Kp, kp = idx - ang * Kp;
+        long long b = b0 + ang; if (b >= a.nb) b = a.nb - 1;
+        double sn, cs;
+        sincos(sMu[kp] * a.beta[b], &sn, &cs);
+        const double w = sW[kp];
+        const int row = k2_trig_row(ang);
+        tc[row * ldt + kp] = w * cs;
+        ts[row * ldt + kp] = w * sn;
+    }
+}
 
 // Main loop of one warp unit, specialised on the number GC of 16-row groups actually present.
 // acc[class][angle tile][group][even/odd rows][main/alt][frag]; groups >= GC stay untouched (zero).
@@ -214,138 +220,76 @@ __device__ __forceinline__ void k2_mainloop(double (&acc)[2][2][GMAX][2][HALF ? 
     }
 }
 
-// Drain of one staged 16 x span tile of real d: 256 contiguous bytes per store instruction.
-// Staging row ai*8 + ar holds angle 2 ar + ai of the chunk.
-__device__ __forceinline__ void k2_drain_real(const double *buf, double *out, const K2Desc &d, const size_t NN,
-                                              const int lane)
+// ------------------------------------------------------------------------------------------------
+// Complex D (k2_cplx_kernel): 8 warps that compute AND store (the drain multiplies by the per-chunk phase tables;
+// a 56-register store warp is too slow for that: 7.4 vs 5.4 ms at cfg-3).
+// Epilogue of one butterfly result (S = P0 + P1 or D = P0 - P1): staged once per angle tile, every staged value is
+// written to its two mirror targets with the fused phase exp(-i(m alpha + n gamma)) = (ca - i sa)(cg - i sg):
+//     S: (i,i')  m,n >= 0: re = x - y, im = -(z + w)        (ir,i'r) m,n <= 0: re = x - y, im = +(z + w)
+//     D: (i,i'r) m >= 0 >= n: re = x + y, im = w - z         (ir,i')  m <= 0 <= n: re = x + y, im = z - w
+// with x = ca cg, y = sa sg, z = sa cg, w = ca sg for m, n >= 0: the two targets of a tile are complex conjugates
+// up to the sign sigma.  val[ai][g][eo][h]: the butterfly-combined accumulators.
+template <int GMAX>
+__device__ __forceinline__ void k2_emit_cplx(const K2Args &a, const K2Ctx &cx, const double (&val)[2][GMAX][2][2],
+                                             const bool isD, const int qn, const int qbase, const int gcnt)
 {
-#pragma unroll 1
-    for (int hh = 0; hh < 2; ++hh) {
-        const int s = hh * 32 + lane;
-        if (s < d.s_lo || s >= d.s_hi) continue;
-        const double *src = buf + s;
-        double *dst = out + d.e00 + s;
-        const unsigned sb = sigma_bit(d.dib + s);                      // sign sigma(row - col) of this output row
-#pragma unroll
-        for (int ai = 0; ai < 2; ++ai) {
-            const int nrows = ai ? d.nrows1 : d.nrows0;
-            const double *sp = src + ai * 8 * K2_STG_LD;
-            double *dp = dst + (size_t)ai * NN;
-            if (nrows == 8) {                                         // all 8 loads in flight before the stores
-                double v[8];
-#pragma unroll
-                for (int ar = 0; ar < 8; ++ar) v[ar] = sp[ar * K2_STG_LD];
-#pragma unroll
-                for (int ar = 0; ar < 8; ++ar) dp[(size_t)(2 * ar) * NN] = flip(v[ar], sb);
-            } else {
-                for (int ar = 0; ar < nrows; ++ar) dp[(size_t)(2 * ar) * NN] = flip(sp[ar * K2_STG_LD], sb);
-            }
-        }
-    }
-}
-
-// Epilogue of one mirror target: stage the 16 x span tile (signs applied), then hand it to the store warp
-// (real d) or drain it here with the fused phase (complex D).
-//   DESC = false: rows ascend with the quadrant row (targets (i,i') and (i,i'r));
-//   DESC = true : rows are the mirrored ones, written in ascending memory order ((ir,i'r) and (ir,i')).
-// val[ai][g][eo][h]: the butterfly-combined accumulators of this target.
-template <bool CPLX, bool DESC, int GMAX>
-__device__ __forceinline__ void k2_store_target(const K2Args &a, K2Ctx &cx, const double (&val)[2][GMAX][2][2],
-                                                const int col, const int qbase, const int gcnt)
-{
-    const int N = cx.N, Q = cx.Q, i0 = cx.i0, zskip = cx.zskip, lane = cx.lane, r = cx.r, c = cx.c;
-    const int span = 16 * gcnt;
-    // staging position s <-> global row: ascending i0+qbase+s ; descending (N-1-i0-qbase-(span-1)) + s
-    const int row0 = DESC ? (N - 1 - i0 - qbase - (span - 1)) : (i0 + qbase);
-    // valid staging positions [s_lo, s_hi): quadrant row < Q, and (mirrored rows) quadrant row >= zskip
-    const int s_lo = DESC ? max(0, qbase + span - Q) : 0;
-    const int s_hi = DESC ? min(span, qbase + span - zskip) : min(span, Q - qbase);
-    if (s_hi <= s_lo) return;                                         // warp-uniform
-    // sigma(row - col) of the lane's element t: row - col = +-(16g + 4c + t) + const, only mod 4 matters
-    const int dib = DESC ? (N - 1 - i0 - qbase - col) : (i0 + qbase - col);
-    unsigned sb[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) sb[t] = sigma_bit(DESC ? dib - t : dib + t);
+    const int N = cx.N, Q = cx.Q, i0 = cx.i0, lane = cx.lane;
+    const int ip = i0 + qn, ipr = N - 1 - ip;
+    const int col_a = isD ? ipr : ip, col_d = isD ? ip : ipr;       // S: (i,i') up, (ir,i'r) down;  D: (i,i'r) up, (ir,i') down
+    const bool both = qn >= cx.zskip;                               // n = 0 mirrors onto itself
+    const bool on_a = !isD || both, on_d0 = isD || both;
+    const int row_a = i0 + qbase, row_d = N - 1 - i0 - qbase;
+    const int s_hi = min(16 * gcnt, Q - qbase), s_lo_d = max(0, cx.zskip - qbase);
+    const int dib_a = row_a - col_a, dib_d = row_d - col_d;
     const size_t NN = (size_t)N * N;
-    const size_t e00 = (size_t)cx.b0 * NN + (size_t)col * N + row0;   // angle 0 of the chunk, staging position 0
+    double2 *out = reinterpret_cast<double2 *>(a.out);
     double *buf = cx.stg;
-    if constexpr (!CPLX) {
-        mbar_wait(cx.empty, (cx.tiles & 1) ^ 1);                     // the store warp has drained the previous tile
-        if (lane == 0) {
-            K2Desc d;
-            d.e00 = e00; d.s_lo = s_lo; d.s_hi = s_hi;
-            d.nrows0 = (int)max(0LL, min(8LL, (a.nb - cx.b0 + 1) / 2));
-            d.nrows1 = (int)max(0LL, min(8LL, (a.nb - cx.b0) / 2));
-            d.dib = (row0 - col) & 3; d.pad = 0;
-            *cx.desc = d;
-        }
 #pragma unroll
-        for (int ai = 0; ai < 2; ++ai) {
+    for (int ai = 0; ai < 2; ++ai) {
+        const long long bf = cx.b0 + ai;                              // first angle of the tile
+        if (bf >= a.nb) break;                                        // warp-uniform
+        const int nrows = (int)min(8LL, (a.nb - bf + 1) / 2);
+        __syncwarp();                                                 // the previous drain has read the buffer
+        {
+            double *p = buf + cx.r * K2_STG_LD + 4 * cx.c;            // the lane owns rows 16g+4c .. 16g+4c+3 of the unit
 #pragma unroll
             for (int g = 0; g < GMAX; ++g) {
                 if (g < gcnt) {
-                    // the lane owns rows 16g+4c .. 16g+4c+3 of the unit: (even tile, odd tile) interleaved; the store
-                    // warp applies the sign sigma
-                    const double v0 = val[ai][g][0][0], v1 = val[ai][g][1][0], v2 = val[ai][g][0][1], v3 = val[ai][g][1][1];
-                    double *p = buf + (ai * 8 + r) * K2_STG_LD + (DESC ? (span - 4) - 16 * g - 4 * c : 16 * g + 4 * c);
-                    reinterpret_cast<double2 *>(p)[0] = DESC ? make_double2(v3, v2) : make_double2(v0, v1);
-                    reinterpret_cast<double2 *>(p)[1] = DESC ? make_double2(v1, v0) : make_double2(v2, v3);
+                    reinterpret_cast<double2 *>(p + 16 * g)[0] = make_double2(val[ai][g][0][0], val[ai][g][1][0]);
+                    reinterpret_cast<double2 *>(p + 16 * g)[1] = make_double2(val[ai][g][0][1], val[ai][g][1][1]);
                 }
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(cx.full);                          // release: tile + descriptor are visible
-        ++cx.tiles;
-    } else {
-    // complex D: one angle tile (8 rows) at a time: stage with the sign applied, then drain with the fused phase
-    // exp(-i(m alpha + n gamma)) = (ca - i sa)(cg - i sg); m -> -m flips sa, n -> -n flips sg
-#pragma unroll
-    for (int ai = 0; ai < 2; ++ai) {
-        const long long bfirst = cx.b0 + ai;
-        if (bfirst >= a.nb) break;                                    // warp-uniform
-        const int nrows = (int)min(8LL, (a.nb - bfirst + 1) / 2);
-        __syncwarp();
-#pragma unroll
-        for (int g = 0; g < GMAX; ++g) {
-            if (g < gcnt) {
-                const double v0 = flip(val[ai][g][0][0], sb[0]), v1 = flip(val[ai][g][1][0], sb[1]);
-                const double v2 = flip(val[ai][g][0][1], sb[2]), v3 = flip(val[ai][g][1][1], sb[3]);
-                double *p = buf + r * K2_STG_LD + (DESC ? (span - 4) - 16 * g - 4 * c : 16 * g + 4 * c);
-                reinterpret_cast<double2 *>(p)[0] = DESC ? make_double2(v3, v2) : make_double2(v0, v1);
-                reinterpret_cast<double2 *>(p)[1] = DESC ? make_double2(v1, v0) : make_double2(v2, v3);
-            }
-        }
-        __syncwarp();
+        const double *pg = cx.sPh + (2 * K2_ANG + ai) * Q + qn;       // cos(n gamma) of angle ai; sin at + K2_ANG rows
+        double2 *base_a = out + (size_t)bf * NN + (size_t)col_a * N + row_a;
+        double2 *base_d = out + (size_t)bf * NN + (size_t)col_d * N + row_d;
 #pragma unroll 1
-        for (int hh = 0; hh * 32 < span; ++hh) {
-            const int s = hh * 32 + lane;
-            if (s < s_lo || s >= s_hi) continue;
-            const int row = row0 + s;
-            const bool mneg = row < i0, nneg = col < i0;
-            const int qr = mneg ? (N - 1 - row - i0) : (row - i0);
-            const int qc = nneg ? (N - 1 - col - i0) : (col - i0);
-            const double *pa = cx.sPh + ai * Q + qr, *pg = cx.sPh + (2 * K2_ANG + ai) * Q + qc;
+        for (int s = lane; s < s_hi; s += 32) {
+            const double *pa = cx.sPh + ai * Q + qbase + s;           // cos(m alpha) of angle ai; sin at + K2_ANG rows
             const double *sp = buf + s;
-            double2 *dst = reinterpret_cast<double2 *>(a.out) + e00 + (size_t)ai * NN + s;
+            const bool on_d = on_d0 && s >= s_lo_d;
+            const unsigned sga = sigma_bit(dib_a + s), sgd = sigma_bit(dib_d - s) ^ 0x80000000u;   // conjugate: im flips
+            double2 *da = base_a + s, *dd = base_d - s;
 #pragma unroll 2
             for (int ar = 0; ar < nrows; ++ar) {                      // angle 2 ar + ai of the chunk
                 const double v = sp[ar * K2_STG_LD];
-                const double ca = pa[(2 * ar) * Q], cg = pg[(2 * ar) * Q];
-                double sa = pa[(K2_ANG + 2 * ar) * Q], sg = pg[(K2_ANG + 2 * ar) * Q];
-                if (mneg) sa = -sa;
-                if (nneg) sg = -sg;
-                const double cr = ca * cg - sa * sg;
-                const double ci = -(sa * cg + ca * sg);
-                dst[(size_t)(2 * ar) * NN] = make_double2(v * cr, v * ci);
+                const double ca = pa[(2 * ar) * Q], sa = pa[(K2_ANG + 2 * ar) * Q];
+                const double cg = pg[(2 * ar) * Q], sg = pg[(K2_ANG + 2 * ar) * Q];
+                const double x = ca * cg, y = sa * sg, z = sa * cg, w = ca * sg;
+                const double re = isD ? x + y : x - y;
+                const double im = isD ? w - z : -(z + w);
+                const double vr = v * re, vi = v * im;
+                if (on_a) da[(size_t)(2 * ar) * NN] = make_double2(flip(vr, sga), flip(vi, sga));
+                if (on_d) dd[(size_t)(2 * ar) * NN] = make_double2(flip(vr, sgd ^ 0x80000000u), flip(vi, sgd));
             }
         }
-    }
     }
 }
 
 // One warp unit: quadrant column qn, gcnt groups of 16 quadrant rows starting at group g0, 16 angles.
-template <bool HALF, bool CPLX>
-__device__ __forceinline__ void k2_unit(const K2Args &a, K2Ctx &cx, const int qn, const int g0, const int gcnt)
+template <bool HALF>
+__device__ __forceinline__ void k2_unit_cplx(const K2Args &a, const K2Ctx &cx, const int qn, const int g0, const int gcnt)
 {
     constexpr int GMAX = HALF ? 2 : 4;
     constexpr int NALT = HALF ? 2 : 1;
@@ -364,9 +308,7 @@ __device__ __forceinline__ void k2_unit(const K2Args &a, K2Ctx &cx, const int qn
         default: k2_mainloop<HALF, GMAX, 1>(acc, cx, qn, g0); break;
         }
     }
-
-    // ---- epilogue ---------------------------------------------------------------------------------------
-    // butterfly, once: sum = P0 + P1 (targets (i,i'), (ir,i'r)), dif = P0 - P1 (targets (ir,i'), (i,i'r));
+    // butterfly, once: S = P0 + P1 (targets (i,i'), (ir,i'r)), D = P0 - P1 (targets (ir,i'), (i,i'r));
     // for half-integer j the mirrored pair uses the accumulators of the other trig function (alt).
     double vs[2][GMAX][2][2], vd[2][GMAX][2][2];
 #pragma unroll
@@ -380,49 +322,24 @@ __device__ __forceinline__ void k2_unit(const K2Args &a, K2Ctx &cx, const int qn
                     vs[ai][g][eo][h] = acc[0][ai][g][eo][0][h] + acc[1][ai][g][eo][0][h];
                     vd[ai][g][eo][h] = acc[0][ai][g][eo][NALT - 1][h] - acc[1][ai][g][eo][NALT - 1][h];
                 }
-    const int ip = cx.i0 + qn, ipr = cx.N - 1 - ip;
-    const int qbase = 16 * g0;                     // first quadrant row of the unit
-    k2_store_target<CPLX, false, GMAX>(a, cx, vs, ip, qbase, gcnt);                 // ( i, i')
-    k2_store_target<CPLX, true, GMAX>(a, cx, vd, ip, qbase, gcnt);                  // (ir, i')
-    if (qn >= cx.zskip) {                          // n = 0 mirrors onto itself (warp-uniform)
-        k2_store_target<CPLX, true, GMAX>(a, cx, vs, ipr, qbase, gcnt);             // (ir, i'r)
-        k2_store_target<CPLX, false, GMAX>(a, cx, vd, ipr, qbase, gcnt);            // ( i, i'r)
-    }
+    k2_emit_cplx<GMAX>(a, cx, vs, false, qn, 16 * g0, gcnt);
+    k2_emit_cplx<GMAX>(a, cx, vd, true, qn, 16 * g0, gcnt);
 }
 
-// Store warp q (real-d kernels): drains the staged tiles of compute warp q until that warp has finished.
-__device__ __forceinline__ void k2_store_warp(const K2Args &a, const double *buf, const K2Desc *desc, void *full,
-                                              void *empty, const int lane)
-{
-    const size_t NN = (size_t)a.p.N * a.p.N;
-    unsigned phase = 0u;
-    for (;;) {
-        mbar_wait(full, phase);                                       // acquire: tile + descriptor are visible
-        const K2Desc d = *desc;
-        if (d.s_hi < 0) break;
-        k2_drain_real(buf, a.out, d, NN, lane);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty);                            // release: the buffer may be overwritten
-        phase ^= 1u;
-    }
-}
-
-template <bool HALF, bool CPLX>
-__global__ void __launch_bounds__(k2_threads(CPLX), 1) k2_dmma_kernel(K2Args a)
+template <bool HALF>
+__global__ void __launch_bounds__(K2_THREADS_CPLX, 1) k2_cplx_kernel(K2Args a)
 {
     constexpr int GMAX = HALF ? 2 : 4;
-    constexpr int NT = k2_threads(CPLX);                   // all threads (setup phase)
-    constexpr int NC = K2_CWARPS * 32;                     // compute threads
+    constexpr int NC = K2_CWARPS * 32;
     extern __shared__ __align__(16) double sm[];
     const PlanDev &p = a.p;
     const int Q = p.Q, Kp = p.Kp, ldu = p.ldu;
-    const int nsub = CPLX ? 1 : a.nsub;                    // 16-angle chunks per barrier phase ("super-chunk")
-    const K2Smem L = k2_smem_layout(Q, Kp, ldu, CPLX, nsub);
+    const K2Smem L = k2_smem_layout(Q, Kp, ldu);
     const int ldt = L.ldt;
     double *sUQ = sm + L.uq, *sMu = sm + L.mu, *sW = sm + L.w, *sTc = sm + L.tc, *sTs = sm + L.ts;
     double *sPh = sm + L.ph;
-    void *uq_bar = sm + L.bars + 2 * K2_CWARPS;
-    int *sCounter = reinterpret_cast<int *>(sm + L.bars + 2 * K2_CWARPS + 1);
+    void *uq_bar = sm + L.bars;
+    int *sCounter = reinterpret_cast<int *>(sm + L.bars + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // one-time: UQ -> shared through the TMA engine (one bulk copy, mbarrier-signalled); zero pad rows, mu, w by hand
@@ -430,44 +347,27 @@ __global__ void __launch_bounds__(k2_threads(CPLX), 1) k2_dmma_kernel(K2Args a)
         const unsigned uq_bytes = (unsigned)(Q * ldu) * 8u;        // a multiple of 16: ldu is even
         if (tid == 0) {
             mbar_init(uq_bar, 1);
-            for (int w = 0; w < 2 * K2_CWARPS; ++w) mbar_init(sm + L.bars + w, 1);
             mbar_init_fence();
             mbar_expect_tx(uq_bar, uq_bytes);
             bulk_load(sUQ, p.uq, uq_bytes, uq_bar);
         }
-        for (int i = Q * ldu + tid; i < L.qpad * ldu; i += NT) sUQ[i] = 0.0;
-        for (int i = tid; i < Kp; i += NT) { sMu[i] = p.mu[i]; sW[i] = p.w[i]; }
-        __syncthreads();                                           // the mbarriers are initialised for everybody
+        for (int i = Q * ldu + tid; i < L.qpad * ldu; i += NC) sUQ[i] = 0.0;
+        for (int i = tid; i < Kp; i += NC) { sMu[i] = p.mu[i]; sW[i] = p.w[i]; }
+        __syncthreads();                                           // the mbarrier is initialised for everybody
         mbar_wait(uq_bar, 0);
-    }
-
-    if (!CPLX) {
-        // warp specialisation: give the registers of the store warpgroup to the two compute warpgroups
-        if (warp >= K2_CWARPS) {
-            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(K2_REGS_STORE));
-            const int q = warp - K2_CWARPS;
-            k2_store_warp(a, sm + L.stg + q * (K2_STG_ROWS * K2_STG_LD),
-                          reinterpret_cast<const K2Desc *>(sm + L.desc + q * (int)(sizeof(K2Desc) / 8)), sm + L.bars + q,
-                          sm + L.bars + K2_CWARPS + q, lane);
-            return;
-        }
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(K2_REGS_COMPUTE));
     }
 
     K2Ctx cx;
     cx.sUQ = sUQ; cx.sTc = sTc; cx.sTs = sTs; cx.sPh = sPh;
-    cx.stg = sm + L.stg + warp * (L.stg_rows * K2_STG_LD);
-    cx.desc = reinterpret_cast<K2Desc *>(sm + L.desc + warp * (int)(sizeof(K2Desc) / 8));
-    cx.full = sm + L.bars + warp; cx.empty = sm + L.bars + K2_CWARPS + warp;
+    cx.stg = sm + L.stg + warp * (K2_HT_ROWS * K2_STG_LD);
     cx.ldu = ldu; cx.ldt = ldt; cx.N = p.N; cx.Q = Q; cx.i0 = p.N - Q; cx.zskip = p.zskip;
     cx.Kp = Kp; cx.K0p = p.K0p; cx.twoj = p.twoj;
     cx.lane = lane; cx.r = lane >> 2; cx.c = lane & 3;
-    cx.tiles = 0;
-    // Anti-phase scheduling of the two compute warps (w, w+4) that share an SM sub-partition and hence one DMMA pipe:
-    // a warp may start a main loop only after its partner has passed the MIDPOINT of its own (one token, a pair of
-    // named barriers), so the main loops overlap pairwise by half and the epilogues of the pair never coincide.
-    // (Left alone the pair locks into phase: the warp that is alone in its main loop runs faster than half speed, so
-    // any offset shrinks, and then both are in their epilogues while the pipe idles.)  Measured: 11.4 -> 10.7 ms.
+    // Anti-phase scheduling of the two warps (w, w+4) that share an SM sub-partition and hence one DMMA pipe: a warp
+    // may start a main loop only after its partner has passed a release point of its own (one token, a pair of named
+    // barriers), so the main loops overlap only partly and the epilogues of the pair never coincide.  (Left alone the
+    // pair locks into phase: the warp that is alone in its main loop runs faster than half speed, so any offset
+    // shrinks, and then both are in their epilogues while the pipe idles.)
     cx.krel = a.handoff - 1;
     cx.bar_me = a.handoff ? 2 + warp : 0;
     cx.bar_other = a.handoff ? 2 + (warp ^ 4) : 0;
@@ -477,51 +377,34 @@ __global__ void __launch_bounds__(k2_threads(CPLX), 1) k2_dmma_kernel(K2Args a)
     const int upc = (ngroups + GMAX - 1) / GMAX;          // parts per column
     const int gbase = ngroups / upc, grem = ngroups - gbase * upc;   // the first grem parts have gbase+1 groups
     const int nunits = Q * upc;
-    const int sang = K2_ANG * nsub;                        // angles per barrier phase
-    const long long nchunks = (a.nb + sang - 1) / sang;
+    const long long nchunks = (a.nb + K2_ANG - 1) / K2_ANG;
 
     // work item = (chunk, split): small batches are split over several CTAs per chunk so that the whole GPU is used
     const int nsplit = max(1, a.nsplit);
     for (long long item = blockIdx.x; item < nchunks * nsplit; item += gridDim.x) {
         const long long ch = item / nsplit;
         const int split = (int)(item - ch * nsplit);
-        const long long b0 = ch * sang;
-        const int nsub_here = (int)min((long long)nsub, (a.nb - b0 + K2_ANG - 1) / K2_ANG);
+        const long long b0 = ch * K2_ANG;
         cx.b0 = b0;
-        named_bar_sync(1, NC);                             // compute warps: previous chunk's table readers are done
-        const int ntot = nunits * nsub_here;
-        const int u_begin = (int)((long long)ntot * split / nsplit), u_end = (int)((long long)ntot * (split + 1) / nsplit);
+        named_bar_sync(1, NC);                             // the previous chunk's table readers are done
+        const int u_begin = (int)((long long)nunits * split / nsplit), u_end = (int)((long long)nunits * (split + 1) / nsplit);
         if (tid == 0) *sCounter = u_begin;
+        k2_trig_fill(a, sMu, sW, sTc, ldt, Kp, b0, tid, NC);
 #pragma unroll 1
-        for (int idx = tid; idx < sang * Kp; idx += NC) {
-            const int ang = idx / Kp, kp = idx - ang * Kp;
+        for (int idx = tid; idx < 2 * K2_ANG * Q; idx += NC) {
+            const int which = idx / (K2_ANG * Q), rem = idx - which * (K2_ANG * Q);
+            const int ang = rem / Q, q = rem - ang * Q;
             long long b = b0 + ang; if (b >= a.nb) b = a.nb - 1;
+            const double m = 0.5 * (double)(2 * q + (p.twoj & 1));
             double s, cs;
-            sincos(sMu[kp] * a.beta[b], &s, &cs);         // fl(mu*beta) then sincos, like :199
-            const double w = sW[kp];
-            const int row = (ang & ~(K2_ANG - 1)) + k2_trig_row(ang & (K2_ANG - 1));
-            sTc[row * ldt + kp] = w * cs;
-            sTs[row * ldt + kp] = w * s;
-        }
-        if (CPLX) {
-#pragma unroll 1
-            for (int idx = tid; idx < 2 * K2_ANG * Q; idx += NC) {
-                const int which = idx / (K2_ANG * Q), rem = idx - which * (K2_ANG * Q);
-                const int ang = rem / Q, q = rem - ang * Q;
-                long long b = b0 + ang; if (b >= a.nb) b = a.nb - 1;
-                const double m = 0.5 * (double)(2 * q + (p.twoj & 1));
-                double s, cs;
-                sincos(m * (which ? a.gamma[b] : a.alpha[b]), &s, &cs);
-                sPh[((2 * which + 0) * K2_ANG + ang) * Q + q] = cs;
-                sPh[((2 * which + 1) * K2_ANG + ang) * Q + q] = s;
-            }
+            sincos(m * (which ? a.gamma[b] : a.alpha[b]), &s, &cs);
+            sPh[((2 * which + 0) * K2_ANG + ang) * Q + q] = cs;
+            sPh[((2 * which + 1) * K2_ANG + ang) * Q + q] = s;
         }
         named_bar_sync(1, NC);
 
-        // dynamic unit scheduler (one shared counter per chunk): unit v -> part v % upc of column v / upc.  The
-        // eight warps then work on adjacent columns, whose output is adjacent in memory: the 16 matrices of the
-        // chunk are written as (two) sequential streams each, which is what the L2/HBM write path needs -- the
-        // same bytes written as scattered 512-byte runs sustain only ~3.2 TB/s (tools/store_pattern_mb.cu)
+        // dynamic unit scheduler (one shared counter per chunk): unit v -> part v % upc of column v / upc: the eight
+        // warps work on adjacent columns, whose output is adjacent in memory
 #pragma unroll 1
         for (;;) {
             if (cx.bar_me) named_bar_sync(cx.bar_me, 64);
@@ -529,26 +412,11 @@ __global__ void __launch_bounds__(k2_threads(CPLX), 1) k2_dmma_kernel(K2Args a)
             if (lane == 0) v = atomicAdd(sCounter, 1);
             v = __shfl_sync(0xffffffffu, v, 0);
             if (v >= u_end) { if (cx.bar_other) named_bar_arrive(cx.bar_other, 64); break; }
-            const int sub = v / nunits;                            // which 16-angle chunk of the phase
-            v -= sub * nunits;
-            cx.b0 = b0 + sub * K2_ANG;
-            cx.sTc = sTc + sub * K2_ANG * ldt; cx.sTs = sTs + sub * K2_ANG * ldt;
-            const int qn = v / upc, part = v - qn * upc;           // column-major unit order: see the store-locality note
+            const int qn = v / upc, part = v - qn * upc;
             const int g0 = part * gbase + min(part, grem);
             const int gcnt = gbase + (part < grem ? 1 : 0);
-            k2_unit<HALF, CPLX>(a, cx, qn, g0, gcnt);
+            k2_unit_cplx<HALF>(a, cx, qn, g0, gcnt);
         }
-    }
-    if (!CPLX) {
-        // tell the store warp that this compute warp has finished
-        mbar_wait(cx.empty, (cx.tiles & 1) ^ 1);
-        if (lane == 0) {
-            K2Desc d;
-            d.e00 = 0; d.s_lo = 0; d.s_hi = -1; d.nrows0 = d.nrows1 = 0; d.dib = 0; d.pad = 0;
-            *cx.desc = d;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(cx.full);
     }
 }
 
@@ -566,8 +434,6 @@ __global__ void __launch_bounds__(k2_threads(CPLX), 1) k2_dmma_kernel(K2Args a)
 //   * the last, partial wave of chunks is split over several CTAs each (K2Args::tsplit).
 // ------------------------------------------------------------------------------------------------
 constexpr int K2_TILE_ASC = 1, K2_TILE_DESC = 2, K2_TILE_END_ALL = 8;
-constexpr int K2_HT_ROWS = 8;                              // angles per staged half tile
-constexpr int K2_HT_SIZE = K2_HT_ROWS * K2_STG_LD;         // doubles per ring slot
 
 struct K2Tile {                 // descriptor of one staged half tile: 8 angles (one MMA row tile) x <= 64 quadrant rows
     unsigned long long ea;      // ascending target : element index of (first angle, position 0); position s lives at ea + s
@@ -618,24 +484,6 @@ __device__ __forceinline__ K2Item k2_item(const K2Args &a, const long long it, c
     o.u_begin = (int)((long long)nunits * split / a.tsplit);
     o.u_end = (int)((long long)nunits * (split + 1) / a.tsplit);
     return o;
-}
-
-// trig tables of one chunk: Tc/Ts[row(angle)][kp] = w cos|sin(mu beta), fl(mu*beta) then sincos like src/WignerD.jl:199
-__device__ __forceinline__ void k2_trig_fill(const K2Args &a, const double *sMu, const double *sW, double *tc, const int ldt,
-                                             const int Kp, const long long b0, const int t0, const int nt)
-{
-    double *ts = tc + K2_ANG * ldt;
-#pragma unroll 1
-    for (int idx = t0; idx < K2_ANG * Kp; idx += nt) {
-        const int ang = idx / Kp, kp = idx - ang * Kp;
-        long long b = b0 + ang; if (b >= a.nb) b = a.nb - 1;
-        double sn, cs;
-        sincos(sMu[kp] * a.beta[b], &sn, &cs);
-        const double w = sW[kp];
-        const int row = k2_trig_row(ang);
-        tc[row * ldt + kp] = w * cs;
-        ts[row * ldt + kp] = w * sn;
-    }
 }
 
 struct K2RCtx {                 // what a compute warp needs for its hand-offs
@@ -724,17 +572,20 @@ __device__ __forceinline__ void k2_drain_pair(const double *buf, double *out, co
             double *q[K2_HT_ROWS];
 #pragma unroll
             for (int ar = 0; ar < K2_HT_ROWS; ++ar) v[ar] = sp[ar * K2_STG_LD];
+            // signs are applied in place (one LOP3 on the high word per value and target, no register copies)
+#pragma unroll
+            for (int ar = 0; ar < K2_HT_ROWS; ++ar) v[ar] = flip(v[ar], sa);
             if (on_a) {
 #pragma unroll
                 for (int ar = 0; ar < K2_HT_ROWS; ++ar) q[ar] = pa + ar * step;
 #pragma unroll
-                for (int ar = 0; ar < K2_HT_ROWS; ++ar) *q[ar] = flip(v[ar], sa);
+                for (int ar = 0; ar < K2_HT_ROWS; ++ar) *q[ar] = v[ar];
             }
             if (on_d) {
 #pragma unroll
-                for (int ar = 0; ar < K2_HT_ROWS; ++ar) q[ar] = pd + ar * step;
+                for (int ar = 0; ar < K2_HT_ROWS; ++ar) { q[ar] = pd + ar * step; v[ar] = flip(v[ar], sa ^ sd); }
 #pragma unroll
-                for (int ar = 0; ar < K2_HT_ROWS; ++ar) *q[ar] = flip(v[ar], sd);
+                for (int ar = 0; ar < K2_HT_ROWS; ++ar) *q[ar] = v[ar];
             }
         } else {
 #pragma unroll 1
@@ -745,6 +596,25 @@ __device__ __forceinline__ void k2_drain_pair(const double *buf, double *out, co
                 pa += step; pd += step;
             }
         }
+    }
+}
+
+// Store warp q: drains the 2-slot ring of compute warp q until the END marker.
+//   stg : K2_CWARPS rings of 2 slots;  desc: K2_CWARPS x 2 descriptors;  bars: full[w][slot] then empty[w][slot]
+__device__ __forceinline__ void k2_store_loop(const double *stg, const double *desc_base, unsigned long long *bars, const int q,
+                                              double *out, const size_t NN, const int lane)
+{
+    const double *ring = stg + q * (2 * K2_HT_SIZE);
+    const K2Tile *desc = reinterpret_cast<const K2Tile *>(desc_base) + 2 * q;
+    unsigned long long *full = bars + 2 * q, *empty = bars + 2 * K2_CWARPS + 2 * q;
+    for (unsigned t = 0;; ++t) {
+        const int slot = t & 1;
+        mbar_wait(full + slot, (t >> 1) & 1);                          // acquire: tile + descriptor are visible
+        const K2Tile d = desc[slot];
+        if (d.kind == K2_TILE_END_ALL) break;
+        k2_drain_pair(ring + slot * K2_HT_SIZE, out, d, NN, lane);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + slot);                      // release: the slot may be overwritten
     }
 }
 
@@ -787,10 +657,10 @@ __device__ __forceinline__ void k2_unit_real(const K2Args &a, const K2Ctx &cx, K
 }
 
 template <bool HALF>
-__global__ void __launch_bounds__(k2_threads(false), 1) k2_real_kernel(K2Args a)
+__global__ void __launch_bounds__(K2_THREADS_REAL, 1) k2_real_kernel(K2Args a)
 {
     constexpr int GMAX = HALF ? 2 : 4;
-    constexpr int NT = k2_threads(false);
+    constexpr int NT = K2_THREADS_REAL;
     constexpr int NC = K2_CWARPS * 32;
     extern __shared__ __align__(16) double sm[];
     const PlanDev &p = a.p;
@@ -831,31 +701,17 @@ __global__ void __launch_bounds__(k2_threads(false), 1) k2_real_kernel(K2Args a)
         // ---- store warp q: drains the ring of compute warp q ----
         // (no trig work here: a call -- sincos' slow path -- below setmaxnreg.dec crashes ptxas 12.9)
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(K2_REGS_STORE));
-        const int q = warp - K2_CWARPS;
-        const double *ring = sm + L.stg + q * (2 * K2_HT_SIZE);
-        const K2Tile *desc = reinterpret_cast<const K2Tile *>(sm + L.desc) + 2 * q;
-        unsigned long long *full = bars + 2 * q, *empty = bars + 2 * K2_CWARPS + 2 * q;
-        const size_t NN = (size_t)p.N * p.N;
-        for (unsigned t = 0;; ++t) {
-            const int slot = t & 1;
-            mbar_wait(full + slot, (t >> 1) & 1);                      // acquire: tile + descriptor are visible
-            const K2Tile d = desc[slot];
-            if (d.kind == K2_TILE_END_ALL) break;
-            k2_drain_pair(ring + slot * K2_HT_SIZE, a.out, d, NN, lane);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + slot);                  // release: the slot may be overwritten
-        }
+        k2_store_loop(sm + L.stg, sm + L.desc, bars, warp - K2_CWARPS, a.out, (size_t)p.N * p.N, lane);
         return;
     }
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(K2_REGS_COMPUTE));
 
     K2Ctx cx;
     cx.sUQ = sUQ; cx.sTc = nullptr; cx.sTs = nullptr; cx.sPh = nullptr;
-    cx.stg = nullptr; cx.desc = nullptr; cx.full = nullptr; cx.empty = nullptr;
+    cx.stg = nullptr;
     cx.ldu = ldu; cx.ldt = ldt; cx.N = p.N; cx.Q = Q; cx.i0 = p.N - Q; cx.zskip = p.zskip;
     cx.Kp = Kp; cx.K0p = p.K0p; cx.twoj = p.twoj;
     cx.lane = lane; cx.r = lane >> 2; cx.c = lane & 3;
-    cx.tiles = 0;
     K2RCtx rc;
     rc.stg = sm + L.stg + warp * (2 * K2_HT_SIZE);
     rc.desc = reinterpret_cast<K2Tile *>(sm + L.desc) + 2 * warp;

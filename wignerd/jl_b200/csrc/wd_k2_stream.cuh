@@ -45,9 +45,9 @@ __host__ __device__ inline K2SSmem k2s_smem_layout(bool half)
     s.stage_size = (s.stage_size + 1) & ~1;
     int o = 0;
     s.stage = o; o += K2S_STAGES * s.stage_size;
-    s.stg = o;   o += K2_CWARPS * K2_STG_ROWS * K2_STG_LD;
-    s.desc = o;  o += K2_CWARPS * (int)(sizeof(K2Desc) / 8);
-    s.bars = o;  o += 2 * K2_CWARPS + 2;
+    s.stg = o;   o += K2_CWARPS * 2 * K2_HT_SIZE;                       // a 2-slot half-tile ring per compute warp
+    s.desc = o;  o += K2_CWARPS * 2 * (int)(sizeof(K2Tile) / 8);
+    s.bars = o;  o += 4 * K2_CWARPS;                                     // full[8][2], empty[8][2]
     s.total = o;
     return s;
 }
@@ -137,7 +137,7 @@ __device__ __forceinline__ void k2s_chunk(double (&acc)[2][GMAX][2][HALF ? 2 : 1
 }
 
 template <bool HALF>
-__global__ void __launch_bounds__(k2_threads(false), 1) k2_stream_kernel(K2SArgs sa)
+__global__ void __launch_bounds__(K2_THREADS_REAL, 1) k2_stream_kernel(K2SArgs sa)
 {
     constexpr int GMAX = HALF ? 2 : 4;
     constexpr int NALT = HALF ? 2 : 1;
@@ -150,30 +150,32 @@ __global__ void __launch_bounds__(k2_threads(false), 1) k2_stream_kernel(K2SArgs
     const K2SSmem L = k2s_smem_layout(HALF);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sm + L.bars);
     if (tid == 0) {
-        for (int w = 0; w < 2 * K2_CWARPS; ++w) mbar_init(sm + L.bars + w, 1);
+        for (int w = 0; w < 4 * K2_CWARPS; ++w) mbar_init(bars + w, 1);
         mbar_init_fence();
     }
     __syncthreads();
     if (warp >= K2_CWARPS) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(K2_REGS_STORE));
-        const int q = warp - K2_CWARPS;
-        k2_store_warp(a, sm + L.stg + q * (K2_STG_ROWS * K2_STG_LD),
-                      reinterpret_cast<const K2Desc *>(sm + L.desc + q * (int)(sizeof(K2Desc) / 8)), sm + L.bars + q,
-                      sm + L.bars + K2_CWARPS + q, lane);
+        k2_store_loop(sm + L.stg, sm + L.desc, bars, warp - K2_CWARPS, a.out, (size_t)p.N * p.N, lane);
         return;
     }
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(K2_REGS_COMPUTE));
 
     K2Ctx cx;
     cx.sUQ = nullptr; cx.sTc = nullptr; cx.sTs = nullptr; cx.sPh = nullptr;
-    cx.stg = sm + L.stg + warp * (K2_STG_ROWS * K2_STG_LD);
-    cx.desc = reinterpret_cast<K2Desc *>(sm + L.desc + warp * (int)(sizeof(K2Desc) / 8));
-    cx.full = sm + L.bars + warp; cx.empty = sm + L.bars + K2_CWARPS + warp;
+    cx.stg = nullptr;
+    K2RCtx rc;
+    rc.stg = sm + L.stg + warp * (2 * K2_HT_SIZE);
+    rc.desc = reinterpret_cast<K2Tile *>(sm + L.desc) + 2 * warp;
+    rc.full = bars + 2 * warp; rc.empty = bars + 2 * K2_CWARPS + 2 * warp;
+    rc.tiles = 0;
+    rc.NN = (size_t)p.N * p.N;
     cx.ldu = ldu; cx.ldt = 0; cx.N = p.N; cx.Q = Q; cx.i0 = p.N - Q; cx.zskip = p.zskip;
     cx.Kp = p.Kp; cx.K0p = p.K0p; cx.twoj = p.twoj;
     cx.lane = lane; cx.r = lane >> 2; cx.c = lane & 3;
-    cx.tiles = 0; cx.bar_me = 0; cx.bar_other = 0;
+    cx.bar_me = 0; cx.bar_other = 0;
     const int r = cx.r, c = cx.c;
 
     const int ngroups = (Q + 15) >> 4;
@@ -188,6 +190,10 @@ __global__ void __launch_bounds__(k2_threads(false), 1) k2_stream_kernel(K2SArgs
         const int rb = (int)((tile / ncb) % nrb);
         const long long ac = tile / ((long long)ncb * nrb);
         cx.b0 = ac * K2_ANG;
+        rc.e_item = (size_t)cx.b0 * rc.NN;
+        rc.nrows0 = (int)min(8LL, (a.nb - cx.b0 + 1) / 2);
+        rc.nrows1 = (int)min(8LL, (a.nb - cx.b0) / 2);
+        rc.ntiles = rc.nrows1 > 0 ? 2 : 1;
         const int g0 = rb * GMAX, gcnt = min(GMAX, ngroups - g0);
         const int qn = cb * K2_CWARPS + warp;
         const bool active = qn < Q;
@@ -246,7 +252,7 @@ __global__ void __launch_bounds__(k2_threads(false), 1) k2_stream_kernel(K2SArgs
         }
         if (!active) continue;
 
-        // ---- epilogue: identical to the resident kernel ------------------------------------------------------
+        // ---- epilogue: the resident real-d kernel's (k2_emit: S and D staged once each, two mirror targets per tile) ----
         double vs[2][GMAX][2][2], vd[2][GMAX][2][2];
 #pragma unroll
         for (int ai = 0; ai < 2; ++ai)
@@ -259,25 +265,13 @@ __global__ void __launch_bounds__(k2_threads(false), 1) k2_stream_kernel(K2SArgs
                         vs[ai][g][eo][h] = acc[0][ai][g][eo][0][h] + acc[1][ai][g][eo][0][h];
                         vd[ai][g][eo][h] = acc[0][ai][g][eo][NALT - 1][h] - acc[1][ai][g][eo][NALT - 1][h];
                     }
-        const int ip = cx.i0 + qn, ipr = cx.N - 1 - ip;
-        const int qbase = 16 * g0;
-        k2_store_target<false, false, GMAX>(a, cx, vs, ip, qbase, gcnt);
-        k2_store_target<false, true, GMAX>(a, cx, vd, ip, qbase, gcnt);
-        if (qn >= cx.zskip) {
-            k2_store_target<false, true, GMAX>(a, cx, vs, ipr, qbase, gcnt);
-            k2_store_target<false, false, GMAX>(a, cx, vd, ipr, qbase, gcnt);
-        }
+        rc.e_ip = rc.e_item + (size_t)(cx.i0 + qn) * cx.N;
+        rc.e_ipr = rc.e_item + (size_t)(cx.N - 1 - cx.i0 - qn) * cx.N;
+        k2_emit<GMAX>(a, cx, rc, vs, false, qn, 16 * g0, gcnt);
+        k2_emit<GMAX>(a, cx, rc, vd, true, qn, 16 * g0, gcnt);
     }
     cp_async_wait<0>();
-    // tell the store warp that this compute warp has finished
-    mbar_wait(cx.empty, (cx.tiles & 1) ^ 1);
-    if (lane == 0) {
-        K2Desc d;
-        d.e00 = 0; d.s_lo = 0; d.s_hi = -1; d.nrows0 = d.nrows1 = 0; d.dib = 0; d.pad = 0;
-        *cx.desc = d;
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(cx.full);
+    k2_send_marker(cx, rc, K2_TILE_END_ALL);                  // tell the store warp that this compute warp has finished
 }
 
 }  // namespace wd

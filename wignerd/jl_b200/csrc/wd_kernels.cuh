@@ -145,8 +145,7 @@ struct K2Args {
     double *out;                          // nb * N*N doubles (or * 2 for complex)
     int equator;                          // apply the exact zeros of :230-237 (plain kernel only)
     int handoff;                          // DMMA kernel: midpoint hand-off between paired compute warps
-    int nsub;                             // DMMA kernel: 16-angle chunks per barrier phase (1 or 2)
-    int nsplit;                           // DMMA kernel: CTAs per chunk (small batches)
+    int nsplit;                           // complex-D DMMA kernel: CTAs per chunk (small batches)
     long long nfull, nitems;              // real-d DMMA kernel: whole-chunk items, all items (k2_item)
     int tsplit;                           // real-d DMMA kernel: CTAs per chunk of the last partial wave
     unsigned long long wrap;              // experiment knob (WD_K2_WRAP=1): run the real-d DMMA kernel without its store instructions
