@@ -154,7 +154,7 @@ def run_reference(args, cfg):
         "impl": "reference", "metric": "wigner_d_elements_per_sec_fp64", "value": value, "unit": "elements/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": cfg["desc"], "twoj": twoj, "sample": sample},
+        "config": {"workload": cfg["desc"], "name": args.config, "twoj": twoj, "sample": sample},
         "cpu_baseline": {"value": value, "unit": "elements/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "C port of src/WignerD.jl:187-206,:266-295 (oracle/wignerd_ref.c); Julia is not installed in this image",
@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--nb", type=int, default=0, help="override angles per GPU (debug)")
     ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 plain FP64-ALU kernel, 2 DMMA kernel")
-    ap.add_argument("--e2e-angles", type=int, default=16384)
+    ap.add_argument("--e2e-angles", type=int, default=0, help="angles per e2e step (0 = the whole workload, nb)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -296,17 +296,34 @@ def main():
     value = elems * world / (ms_per_step * 1e-3)
 
     # ---- e2e: the same call through the public API with HOST buffers (pinned), copies inside the timed region
-    ne = min(args.e2e_angles, nb)
+    # (whole workload per step: 32 GB of pinned host memory at cfg-2; if the host cannot pin that much, a 16384-angle
+    # slice is used instead and the line says so in config.e2e_angles_per_gpu)
+    ne = min(args.e2e_angles, nb) if args.e2e_angles > 0 else nb
+    try:                                   # all ranks of the box pin their buffers at once: keep well inside the host's RAM
+        import psutil
+        need = ne * N * N * (16 if cplx else 8) * int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        if ne > 16384 and psutil.virtual_memory().available < 2 * need:
+            ne = 16384
+    except Exception:
+        pass
+    h_out = None
+    while h_out is None:
+        try:
+            h_out = torch.empty((ne, N, N), dtype=torch.complex128 if cplx else torch.float64).pin_memory()
+        except RuntimeError:
+            if ne <= 16384:
+                raise
+            ne = 16384
+            torch.cuda.empty_cache()
     h_beta = torch.empty(ne, dtype=torch.float64).pin_memory()
     h_beta.copy_(beta[:ne].cpu())
-    h_out = torch.empty((ne, N, N), dtype=torch.complex128 if cplx else torch.float64).pin_memory()
     jv = twoj // 2 if twoj % 2 == 0 else twoj / 2
     if cplx:
         h_a = alpha[:ne].cpu().pin_memory(); h_g = gamma[:ne].cpu().pin_memory()
         e2e_step = lambda: eng.wignerD_batch(jv, h_a.numpy(), h_beta.numpy(), h_g.numpy(), out=h_out.numpy())   # noqa: E731
     else:
         e2e_step = lambda: eng.wignerd_batch(jv, h_beta.numpy(), out=h_out.numpy())                              # noqa: E731
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 10 if ne <= 16384 else 4))
     for _ in range(2):
         e2e_step()
     barrier()
@@ -359,8 +376,9 @@ def main():
     # bandwidth vs the algorithmic flops F_alg = 2 W K nb at the FP64 tensor peak measured in THIS run (cuBLAS DGEMM;
     # MEASURED_PEAKS.json carries no FP64 figure).  Both are reported; "roofline" is the binding one.
     t_step = ms / args.steps * 1e-3
+    kname = "k2_cplx_kernel" if cplx else ("k2_real_kernel" if twoj <= 223 else "k2_stream_kernel")
     rl_hbm = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-              "traffic": traffic, "peak_source": peak_src, "kernel": "k2_dmma_kernel",
+              "traffic": traffic, "peak_source": peak_src, "kernel": kname,
               "algorithmic_bytes_per_launch": bytes_per_launch}
     p64 = fp64.get("cublas_dgemm_tflops") or fp64.get("dmma_loop_tflops")
     line["roofline_hbm"] = rl_hbm
@@ -368,7 +386,7 @@ def main():
     if p64:
         ach64 = f_alg / t_step / 1e12
         rl_t = {"bound": "tensor", "achieved": ach64, "peak": p64, "unit": "TFLOP/s", "frac": ach64 / p64,
-                "traffic": traffic, "kernel": "k2_dmma_kernel", "algorithmic_flops_per_launch": f_alg,
+                "traffic": traffic, "kernel": kname, "algorithmic_flops_per_launch": f_alg,
                 "peak_source": "cuBLAS DGEMM 6144^3 (torch.matmul float64) measured in this run; DMMA.8x8x4 register loop: "
                                f"{fp64.get('dmma_loop_tflops', float('nan')):.1f} TFLOP/s"}
         line["roofline_tensor"] = rl_t

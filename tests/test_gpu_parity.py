@@ -133,6 +133,30 @@ def test_streaming_kernel_vs_plain_and_oracle(engine, twoj, nb):
     assert np.abs(b - o.wignerd_batch(F(twoj, 2), betas)).max() < TOL
 
 
+@pytest.mark.parametrize("twoj", [9, 12, 41])
+def test_multi_wave_ragged_batches(engine, twoj):
+    """more 16-angle chunks than SMs, last chunk ragged: several items per CTA (trig-table double buffer, ring phases
+    across items) and a split last wave in the real-d kernel; complex D alongside.  Every matrix against the plain
+    FP64-ALU kernel, a sample against the oracle."""
+    nb = 148 * 16 * 2 + 16 * 3 + 5
+    rng = np.random.default_rng(twoj)
+    b = rng.uniform(-0.5, pi + 0.5, nb)
+    a, g = rng.uniform(0, 2 * pi, nb), rng.uniform(0, 2 * pi, nb)
+    try:
+        engine.set_variant(1)
+        d1 = engine.wignerd_batch(F(twoj, 2), b).copy()
+        D1 = engine.wignerD_batch(F(twoj, 2), a, b, g).copy()
+    finally:
+        engine.set_variant(0)
+    d0 = engine.wignerd_batch(F(twoj, 2), b)
+    D0 = engine.wignerD_batch(F(twoj, 2), a, b, g)
+    assert np.abs(d0 - d1).max() < 1e-13
+    assert np.abs(D0 - D1).max() < 1e-12
+    pick = np.concatenate([rng.integers(0, nb, 40), [0, nb - 1, nb - 5, nb - 6, 148 * 16, 148 * 16 - 1]])
+    assert np.abs(d0[pick] - o.wignerd_batch(F(twoj, 2), b[pick])).max() < TOL
+    assert np.abs(D0[pick] - o.wignerD_batch(F(twoj, 2), a[pick], b[pick], g[pick])).max() < TOL
+
+
 @pytest.mark.parametrize("twoj", [300, 600, 1024])
 def test_large_j_vs_oracle(engine, twoj):
     betas = np.array([0.0, 0.4, pi / 2, 2.9, pi])
