@@ -114,7 +114,8 @@ int wd_Djmn_batch(wd_handle_t h, const int32_t *twoj, const int32_t *twom, const
 
 /* ---- introspection for tests / benches ------------------------------------------- */
 /* kernel variant selection for wd_d_batch/wd_D_batch: 0 = auto, 1 = force the plain FP64-ALU
- * kernel, 2 = force the DMMA kernel (fails if j does not fit). */
+ * kernel, 2 = force the resident DMMA kernel (fails if the table of j does not fit in shared
+ * memory: 2j > 223), 3 = force the streaming DMMA kernel (real d). */
 int wd_set_variant(wd_handle_t h, int variant);
 /* FP64 micro-benchmarks used to calibrate the roofline (bench.py): returns TFLOP/s of a
  * register-resident DMMA.8x8x4 (kind 0) or DFMA (kind 1) loop over the whole chip. */
