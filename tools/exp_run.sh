@@ -1,10 +1,6 @@
-# kernel-experiment driver: each line = env settings for one short bench run
-run() { cfgname=$1; shift; timeout 300 env "$@" python bench.py --config $cfgname --steps 20 --warmup 3 --no-cpu-baseline --e2e-angles 256 > gpurun_out/b_tmp.log 2>&1; python -c "
-import json,sys
-l=json.loads(open('gpurun_out/b_tmp.log').read().strip().splitlines()[-1]); print(sys.argv[1:], l['ms_per_step'])" $cfgname "$@"; }
-timeout 300 python -m pytest tests -m gpu -x -q -k "multi_wave or D_batch or ref_wignerD or variants" 2>&1 | tail -3
-run cfg3 WD_X=0
-run cfg3 WD_K2_HANDOFF=101
-run cfg3 WD_K2_HANDOFF=102
-run cfg3 WD_K2_HANDOFF=104
-run cfg3 WD_K2_HANDOFF=0
+# guarded experiment driver: quick parity check first (short timeout), then cfg-4
+timeout 90 python tools/quick_check.py > gpurun_out/qc.log 2>&1; rc=$?; echo "quick_check rc=$rc"; tail -5 gpurun_out/qc.log | cut -c1-60
+if [ $rc -ne 0 ]; then echo "stopping"; exit 1; fi
+timeout 100 python bench.py --config cfg4 --steps 5 --warmup 3 > gpurun_out/b_cfg4.log 2>&1; echo "cfg4 rc=$?"; python -c "
+import json
+l=json.loads(open('gpurun_out/b_cfg4.log').read().strip().splitlines()[-1]); print('cfg4', l['ms_per_step'], l['fp64'])"

@@ -3,13 +3,19 @@
 // k2_dmma_kernel (wd_k2_dmma.cuh), but the mu axis is streamed.
 //
 //   CTA tile = 16 angles x one block of 16*GMAX quadrant rows x 8 quadrant columns (one column per compute warp).
-//   The mu axis is cut into chunks of <= 32 columns per eigenvector class; per chunk a stage of a 3-deep ring in
-//   shared memory receives (cp.async, 16-byte granules -> SASS LDGSTS)
+//   The mu axis is cut into chunks of <= 32 columns per eigenvector class; per chunk a stage of a 4-deep ring in
+//   shared memory receives, through the TMA engine (cp.async.bulk, one copy per row -> SASS UBLKCP, completion on the
+//   stage's `full` mbarrier),
 //       - the row block of UQ      [16*GMAX rows][32 (+2 pad)]
 //       - the 8 column rows of UQ  [8][32 (+2 pad)]
 //       - the trig tile            [cos|sin][16 angles][32 (+4 pad)]   from a table precomputed once per call
 //         (k2s_trig_kernel) -- in-kernel trig would be recomputed by every one of the ~Q^2/512 tiles of a chunk.
-//   One named barrier per chunk; accumulators live in registers across the whole mu loop.
+//   Producer/consumer pipeline without CTA barriers: chunk g is loaded by compute warp g % 8 (three chunks ahead,
+//   73 bulk copies = 3 instructions per lane), every compute warp waits on full[stage], and releases the stage by
+//   arriving on empty[stage] (8 arrivals).  The first version -- every thread issuing ~7 cp.async per chunk with
+//   their index arithmetic, cp.async.wait + a CTA named barrier per chunk -- spent 8 % of the compute warps' time in
+//   the issue loop and 3 % at the barrier (ncu source view at j = 410).
+//   Accumulators live in registers across the whole mu loop.
 //   Shared-memory traffic per DMMA equals the resident kernel's; global->shared traffic is ~10 B/clk/SM.
 #pragma once
 #include "wd_k2_dmma.cuh"
@@ -19,7 +25,7 @@ namespace wd {
 constexpr int K2S_KC = 32;                 // mu columns per chunk
 constexpr int K2S_LDU = K2S_KC + 2;        // == 2 mod 4: conflict-free stride-2 row fragments
 constexpr int K2S_LDT = K2S_KC + 4;        // == 4 mod 8: conflict-free 8-row fragments
-constexpr int K2S_STAGES = 3;
+constexpr int K2S_STAGES = 4;
 constexpr int K2S_TRIG_TILE = 2 * K2_ANG * K2S_LDT;       // doubles per (angle chunk, mu chunk) trig tile
 
 __host__ __device__ inline int k2s_nchunks(int Kxp) { return (Kxp + K2S_KC - 1) / K2S_KC; }
@@ -47,7 +53,7 @@ __host__ __device__ inline K2SSmem k2s_smem_layout(bool half)
     s.stage = o; o += K2S_STAGES * s.stage_size;
     s.stg = o;   o += K2_CWARPS * 2 * K2_HT_SIZE;                       // a 2-slot half-tile ring per compute warp
     s.desc = o;  o += K2_CWARPS * 2 * (int)(sizeof(K2Tile) / 8);
-    s.bars = o;  o += 4 * K2_CWARPS;                                     // full[8][2], empty[8][2]
+    s.bars = o;  o += 4 * K2_CWARPS + 2 * K2S_STAGES;                    // ring: full[8][2], empty[8][2]; stages: full[4], empty[4]
     s.total = o;
     return s;
 }
@@ -151,8 +157,10 @@ __global__ void __launch_bounds__(K2_THREADS_REAL, 1) k2_stream_kernel(K2SArgs s
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(sm + L.bars);
+    unsigned long long *sfull = bars + 4 * K2_CWARPS, *sempty = sfull + K2S_STAGES;
     if (tid == 0) {
         for (int w = 0; w < 4 * K2_CWARPS; ++w) mbar_init(bars + w, 1);
+        for (int st = 0; st < K2S_STAGES; ++st) { mbar_init(sfull + st, 1); mbar_init(sempty + st, K2_CWARPS); }
         mbar_init_fence();
     }
     __syncthreads();
@@ -184,6 +192,7 @@ __global__ void __launch_bounds__(K2_THREADS_REAL, 1) k2_stream_kernel(K2SArgs s
     const long long nac = (a.nb + K2_ANG - 1) / K2_ANG;
     const long long ntiles = nac * nrb * ncb;
     const int nck0 = sa.nck0, nck = sa.nck0 + sa.nck1;
+    unsigned gch = 0;                                      // chunks consumed so far by this CTA (ring position / phases)
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int cb = (int)(tile % ncb);
@@ -199,39 +208,40 @@ __global__ void __launch_bounds__(K2_THREADS_REAL, 1) k2_stream_kernel(K2SArgs s
         const bool active = qn < Q;
         const int pe = qn & 1;
 
-        // issue the cp.async copies of mu chunk kc into its ring stage (all compute threads take part)
-        auto issue = [&](const int kc) {
-            double *st = sm + L.stage + (kc % K2S_STAGES) * L.stage_size;
+        // Producer: the whole warp loads mu chunk kc of this tile (global chunk number g) into stage g % STAGES.
+        auto produce = [&](const int kc, const unsigned g) {
+            const int si = (int)(g % K2S_STAGES);
+            const unsigned use = g / K2S_STAGES;
+            if (use > 0) mbar_wait(sempty + si, (use - 1) & 1u);         // all 8 warps are done with the stage's previous chunk
+            double *st = sm + L.stage + si * L.stage_size;
             const int cls = kc >= nck0;
             const int kbase = cls ? p.K0p + (kc - nck0) * K2S_KC : kc * K2S_KC;
             const int kend = cls ? p.Kp : p.K0p;
-            const int gran = min(K2S_KC, kend - kbase) >> 1;            // 16-byte granules per row (widths are multiples of 4)
+            const unsigned wbytes = (unsigned)min(K2S_KC, kend - kbase) * 8u;     // widths are multiples of 4 doubles
+            if (lane == 0) mbar_expect_tx(sfull + si, (unsigned)(ROWS + K2_CWARPS) * wbytes + (unsigned)K2S_TRIG_TILE * 8u);
+            __syncwarp();
             // UQ rows: ROWS of the row block, then the 8 column rows (row indices clamped: values past Q are never stored)
-            for (int i = tid; i < (ROWS + K2_CWARPS) * (K2S_KC / 2); i += NC) {
-                const int row = i / (K2S_KC / 2), g = i - row * (K2S_KC / 2);
-                if (g >= gran) continue;
+            for (int row = lane; row < ROWS + K2_CWARPS; row += 32) {
                 const int q = row < ROWS ? min(16 * g0 + row, Q - 1) : min(cb * K2_CWARPS + (row - ROWS), Q - 1);
-                cp_async16(st + row * K2S_LDU + 2 * g, p.uq + (size_t)q * ldu + kbase + 2 * g);
+                bulk_load(st + row * K2S_LDU, p.uq + (size_t)q * ldu + kbase, wbytes, sfull + si);
             }
-            const double *tsrc = sa.trig + ((size_t)ac * nck + kc) * K2S_TRIG_TILE;
-            for (int i = tid; i < K2S_TRIG_TILE / 2; i += NC) cp_async16(st + L.trig + 2 * i, tsrc + 2 * i);
-            cp_async_commit();
+            if (lane == 0) bulk_load(st + L.trig, sa.trig + ((size_t)ac * nck + kc) * K2S_TRIG_TILE, (unsigned)K2S_TRIG_TILE * 8u, sfull + si);
         };
 
         double acc[2][2][GMAX][2][NALT][2];
 #pragma unroll
         for (int i = 0; i < 2 * 2 * GMAX * 2 * NALT * 2; ++i) (&acc[0][0][0][0][0][0])[i] = 0.0;
 
-        named_bar_sync(1, NC);                              // everybody is done with the previous tile's stages
-        issue(0);
-        if (nck > 1) issue(1); else cp_async_commit();
+        // prologue: the first STAGES-1 chunks of the tile
+        for (int i = 0; i < K2S_STAGES - 1 && i < nck; ++i)
+            if (warp == (int)((gch + i) % K2_CWARPS)) produce(i, gch + i);
 #pragma unroll 1
         for (int kc = 0; kc < nck; ++kc) {
-            cp_async_wait<1>();                             // this thread's copies of chunk kc have landed ...
-            named_bar_sync(1, NC);                          // ... and everybody else's; chunk kc-1 is consumed by all
-            if (kc + 2 < nck) issue(kc + 2); else cp_async_commit();
+            const unsigned g = gch + kc;
+            const int si = (int)(g % K2S_STAGES);
+            mbar_wait(sfull + si, (g / K2S_STAGES) & 1u);                // chunk kc has landed
             if (active) {
-                const double *st = sm + L.stage + (kc % K2S_STAGES) * L.stage_size;
+                const double *st = sm + L.stage + si * L.stage_size;
                 const int cls = kc >= nck0;
                 const int kbase = cls ? p.K0p + (kc - nck0) * K2S_KC : kc * K2S_KC;
                 const int kend = cls ? p.Kp : p.K0p;
@@ -249,7 +259,16 @@ __global__ void __launch_bounds__(K2_THREADS_REAL, 1) k2_stream_kernel(K2SArgs s
                 };
                 if (cls == 0) run(acc[0]); else run(acc[1]);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sempty + si);                      // this warp is done with the stage
+            {
+                // request chunk kc + STAGES-1 (into the stage of chunk kc-1) AFTER the work on chunk kc: by now every warp
+                // has released that stage, the producer does not stall; the copy has two chunks of compute to land
+                const int nx = kc + K2S_STAGES - 1;
+                if (nx < nck && warp == (int)((gch + nx) % K2_CWARPS)) produce(nx, gch + nx);
+            }
         }
+        gch += (unsigned)nck;
         if (!active) continue;
 
         // ---- epilogue: the resident real-d kernel's (k2_emit: S and D staged once each, two mirror targets per tile) ----
@@ -270,7 +289,6 @@ __global__ void __launch_bounds__(K2_THREADS_REAL, 1) k2_stream_kernel(K2SArgs s
         k2_emit<GMAX>(a, cx, rc, vs, false, qn, 16 * g0, gcnt);
         k2_emit<GMAX>(a, cx, rc, vd, true, qn, 16 * g0, gcnt);
     }
-    cp_async_wait<0>();
     k2_send_marker(cx, rc, K2_TILE_END_ALL);                  // tell the store warp that this compute warp has finished
 }
 
