@@ -3,9 +3,5 @@ timeout 120 python __graft_entry__.py --smoke > gpurun_out/smoke_final.log 2>&1;
 if [ $rc -ne 0 ]; then echo "smoke failed: stopping"; exit 1; fi
 timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_final.log 2>&1; rc=$?; echo "pytest rc=$rc"; tail -2 gpurun_out/pytest_gpu_final.log
 if [ $rc -ne 0 ]; then echo "pytest failed: stopping"; exit 1; fi
-timeout 300 python bench.py > gpurun_out/bench_cfg2_final.log 2>&1; echo "bench rc=$?"
-timeout 100 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref_final.log 2>&1; echo "ref rc=$?"
 timeout 100 python bench.py --config cfg4 --steps 5 --warmup 3 > gpurun_out/bench_cfg4_final.log 2>&1; echo "cfg4 rc=$?"
-timeout 60 python bench.py --config cfg1 --steps 100 --no-cpu-baseline > gpurun_out/bench_cfg1_final.log 2>&1; echo "cfg1 rc=$?"
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-angles 16384 > gpurun_out/ncu_list.log 2>&1; echo "ncu list rc=$?"
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:k2_stream -s 300 -c 1 -o gpurun_out/prof_r1_k2_stream_final -f python bench.py --config cfg4 --nb 512 --steps 1 --warmup 3 > gpurun_out/ncu_stream_f.log 2>&1; echo "ncu stream rc=$?"
