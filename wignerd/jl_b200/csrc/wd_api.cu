@@ -48,6 +48,8 @@ constexpr int kMaxTwoJ = 4094;
 struct Plan {
     PlanDev dev{};
     double *uq = nullptr, *mu = nullptr, *w = nullptr;
+    double *uqc = nullptr;          // chunk-major copy of uq for the streaming kernel, built on first use
+    int uqc_qpad = 0;
 };
 
 }  // namespace
@@ -231,8 +233,22 @@ int launch_real(wd_handle_t h, const K2Args &a, size_t smem)
 
 // Streaming DMMA kernel (real d, table too large for shared memory): trig table pass + contraction.
 template <bool HALF>
-int launch_stream(wd_handle_t h, const K2Args &a)
+int launch_stream(wd_handle_t h, const Plan &cpl, const K2Args &a)
 {
+    // chunk-major copy of the table, built once per plan (the plan lives in h->plans; the handle's lock is held)
+    Plan &pl = const_cast<Plan &>(cpl);
+    const int nck0 = k2s_nchunks(a.p.K0p), nck1 = k2s_nchunks(a.p.K1p);
+    if (!pl.uqc) {
+        const int qpad = k2s_qpad(a.p.Q, HALF);
+        const size_t n = (size_t)(nck0 + nck1) * qpad * K2S_LDU;
+        double *buf = nullptr;
+        if (cudaMalloc(&buf, n * sizeof(double)) != cudaSuccess) return fail(WD_ERR_NOMEM, "cudaMalloc of the chunk-major table of 2j = %d failed", a.p.twoj);
+        CU(cudaMemsetAsync(buf, 0, n * sizeof(double), h->stream));
+        const long long total = (long long)(nck0 + nck1) * a.p.Q * K2S_KC;
+        k2s_table_kernel<<<(int)std::min<long long>((total + 255) / 256, (long long)h->num_sms * 8), 256, 0, h->stream>>>(a.p, buf, qpad, nck0, nck1);
+        h->launches++;
+        pl.uqc = buf; pl.uqc_qpad = qpad;
+    }
     const K2SSmem L = k2s_smem_layout(HALF);
     const size_t smem = (size_t)L.total * sizeof(double);
     if (!h->attr_set_stream[HALF]) {
@@ -241,8 +257,8 @@ int launch_stream(wd_handle_t h, const K2Args &a)
     }
     K2SArgs sa;
     sa.base = a;
-    sa.nck0 = k2s_nchunks(a.p.K0p);
-    sa.nck1 = k2s_nchunks(a.p.K1p);
+    sa.nck0 = nck0; sa.nck1 = nck1;
+    sa.uqc = pl.uqc; sa.qpad = pl.uqc_qpad;
     const long long nac = (a.nb + K2_ANG - 1) / K2_ANG;
     const size_t ntrig = (size_t)nac * (sa.nck0 + sa.nck1) * K2S_TRIG_TILE;
     double *trig = nullptr;
@@ -293,13 +309,13 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
     const int variant = h->variant;
     if (variant == 2 && !fits) return fail(WD_ERR_UNSUPPORTED, "2j = %d does not fit the DMMA kernel (%zu B of shared memory)", pl.dev.twoj, smem);
     // Equator() requests (single matrices, exact zeros of :230-237) take the plain kernel
-    if (variant == 3 && !cplx && !equator) return (pl.dev.twoj & 1) ? launch_stream<true>(h, a) : launch_stream<false>(h, a);
+    if (variant == 3 && !cplx && !equator) return (pl.dev.twoj & 1) ? launch_stream<true>(h, pl, a) : launch_stream<false>(h, pl, a);
     const bool use_dmma = !equator && ((variant == 2) || (variant == 0 && fits));
     const bool half = pl.dev.twoj & 1;
     if (use_dmma && !cplx) return half ? launch_real<true>(h, a, smem) : launch_real<false>(h, a, smem);
     if (use_dmma) return half ? launch_cplx<true>(h, a, smem) : launch_cplx<false>(h, a, smem);
     // real d for a table that does not fit in shared memory: the streaming DMMA kernel
-    if (!cplx && !equator && variant != 1) return half ? launch_stream<true>(h, a) : launch_stream<false>(h, a);
+    if (!cplx && !equator && variant != 1) return half ? launch_stream<true>(h, pl, a) : launch_stream<false>(h, pl, a);
     const size_t psm = 2 * (size_t)pl.dev.Kp * sizeof(double);
     const int Q = pl.dev.Q;
     const int gy = std::max(1, std::min(64, (Q * Q + 255) / 256));
@@ -548,7 +564,7 @@ int wd_destroy(wd_handle_t h)
     if (!h) return WD_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (auto &kv : h->plans) cudaFree(kv.second.uq);
+    for (auto &kv : h->plans) { cudaFree(kv.second.uq); if (kv.second.uqc) cudaFree(kv.second.uqc); }
     if (h->d_table) cudaFree(h->d_table);
     if (h->d_flag) cudaFree(h->d_flag);
     if (h->ws_ang) cudaFree(h->ws_ang);
@@ -588,7 +604,7 @@ int wd_cache_clear(wd_handle_t h)
     std::lock_guard<std::mutex> lk(h->mtx);
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (auto &kv : h->plans) cudaFree(kv.second.uq);
+    for (auto &kv : h->plans) { cudaFree(kv.second.uq); if (kv.second.uqc) cudaFree(kv.second.uqc); }
     h->plans.clear();
     h->table_dirty = true;
     return WD_OK;

@@ -4,14 +4,14 @@
 //
 //   CTA tile = 16 angles x one block of 16*GMAX quadrant rows x 8 quadrant columns (one column per compute warp).
 //   The mu axis is cut into chunks of <= 32 columns per eigenvector class; per chunk a stage of a 4-deep ring in
-//   shared memory receives, through the TMA engine (cp.async.bulk, one copy per row -> SASS UBLKCP, completion on the
-//   stage's `full` mbarrier),
+//   shared memory receives, through the TMA engine (cp.async.bulk -> SASS UBLKCP, completion on the stage's `full`
+//   mbarrier; three copies per chunk, from a chunk-major copy of the table that has the stage's row layout),
 //       - the row block of UQ      [16*GMAX rows][32 (+2 pad)]
 //       - the 8 column rows of UQ  [8][32 (+2 pad)]
 //       - the trig tile            [cos|sin][16 angles][32 (+4 pad)]   from a table precomputed once per call
 //         (k2s_trig_kernel) -- in-kernel trig would be recomputed by every one of the ~Q^2/512 tiles of a chunk.
-//   Producer/consumer pipeline without CTA barriers: chunk g is loaded by compute warp g % 8 (three chunks ahead,
-//   73 bulk copies = 3 instructions per lane), every compute warp waits on full[stage], and releases the stage by
+//   Producer/consumer pipeline without CTA barriers: chunk g is requested by compute warp g % 8 (after its work on
+//   chunk g - 3), every compute warp waits on full[stage], and releases the stage by
 //   arriving on empty[stage] (8 arrivals).  The first version -- every thread issuing ~7 cp.async per chunk with
 //   their index arithmetic, cp.async.wait + a CTA named barrier per chunk -- spent 8 % of the compute warps' time in
 //   the issue loop and 3 % at the barrier (ncu source view at j = 410).
@@ -33,8 +33,28 @@ __host__ __device__ inline int k2s_nchunks(int Kxp) { return (Kxp + K2S_KC - 1) 
 struct K2SArgs {
     K2Args base;
     const double *trig;        // [angle chunk][mu chunk][2][16][K2S_LDT]
+    const double *uqc;         // chunk-major copy of UQ: [mu chunk][qpad rows][K2S_LDU], zero on the pads (k2s_table_kernel)
+    int qpad;                  // rows per chunk of uqc: Q rounded up to whole row blocks
     int nck0, nck1;            // mu chunks of class 0 / class 1
 };
+
+// Chunk-major, row-padded copy of a plan's UQ: the row block and the column rows of a mu chunk are then contiguous
+// in global memory in exactly the shared-memory stage layout, so that ONE bulk copy brings each of them in (72 copies
+// of 256 bytes per chunk before: ~12 instructions each on the producing warp, ~9 % of the compute warps' samples).
+__global__ void __launch_bounds__(256) k2s_table_kernel(PlanDev p, double *__restrict__ uqc, int qpad, int nck0, int nck1)
+{
+    const long long total = (long long)(nck0 + nck1) * p.Q * K2S_KC;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int col = (int)(i % K2S_KC);
+        const int q = (int)((i / K2S_KC) % p.Q);
+        const int kc = (int)(i / ((long long)K2S_KC * p.Q));
+        const int cls = kc >= nck0;
+        const int kbase = cls ? p.K0p + (kc - nck0) * K2S_KC : kc * K2S_KC;
+        const int kend = cls ? p.Kp : p.K0p;
+        if (kbase + col < kend) uqc[((size_t)kc * qpad + q) * K2S_LDU + col] = p.uq[(size_t)q * p.ldu + kbase + col];
+    }
+}
+__host__ __device__ inline int k2s_qpad(int Q, bool half) { const int rows = 16 * (half ? 2 : 4); return (Q + rows - 1) / rows * rows; }
 
 struct K2SSmem {               // offsets in doubles
     int stage, stage_size, uqr, uqc, trig, stg, desc, bars, total;
@@ -88,14 +108,6 @@ __global__ void __launch_bounds__(256) k2s_trig_kernel(PlanDev p, const double *
     }
 }
 
-__device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(sdst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // DMMAs of one mu chunk for one class: the two-fragment-set pipeline of k2_mainloop over nsteps k-steps.
 template <bool HALF, int GMAX, int GC>
 __device__ __forceinline__ void k2s_chunk(double (&acc)[2][GMAX][2][HALF ? 2 : 1][2], const double *tA, const double *tB,
@@ -147,7 +159,6 @@ __global__ void __launch_bounds__(K2_THREADS_REAL, 1) k2_stream_kernel(K2SArgs s
 {
     constexpr int GMAX = HALF ? 2 : 4;
     constexpr int NALT = HALF ? 2 : 1;
-    constexpr int NC = K2_CWARPS * 32;
     constexpr int ROWS = 16 * GMAX;
     extern __shared__ __align__(16) double sm[];
     const K2Args &a = sa.base;
@@ -214,18 +225,16 @@ __global__ void __launch_bounds__(K2_THREADS_REAL, 1) k2_stream_kernel(K2SArgs s
             const unsigned use = g / K2S_STAGES;
             if (use > 0) mbar_wait(sempty + si, (use - 1) & 1u);         // all 8 warps are done with the stage's previous chunk
             double *st = sm + L.stage + si * L.stage_size;
-            const int cls = kc >= nck0;
-            const int kbase = cls ? p.K0p + (kc - nck0) * K2S_KC : kc * K2S_KC;
-            const int kend = cls ? p.Kp : p.K0p;
-            const unsigned wbytes = (unsigned)min(K2S_KC, kend - kbase) * 8u;     // widths are multiples of 4 doubles
-            if (lane == 0) mbar_expect_tx(sfull + si, (unsigned)(ROWS + K2_CWARPS) * wbytes + (unsigned)K2S_TRIG_TILE * 8u);
-            __syncwarp();
-            // UQ rows: ROWS of the row block, then the 8 column rows (row indices clamped: values past Q are never stored)
-            for (int row = lane; row < ROWS + K2_CWARPS; row += 32) {
-                const int q = row < ROWS ? min(16 * g0 + row, Q - 1) : min(cb * K2_CWARPS + (row - ROWS), Q - 1);
-                bulk_load(st + row * K2S_LDU, p.uq + (size_t)q * ldu + kbase, wbytes, sfull + si);
+            if (lane == 0) {
+                // three bulk copies: the row block, the 8 column rows (both contiguous in the chunk-major table, pads
+                // included: rows past Q are zero and never stored) and the trig tile
+                constexpr unsigned row_bytes = K2S_LDU * 8u;
+                mbar_expect_tx(sfull + si, (unsigned)(ROWS + K2_CWARPS) * row_bytes + (unsigned)K2S_TRIG_TILE * 8u);
+                const double *src = sa.uqc + (size_t)kc * sa.qpad * K2S_LDU;
+                bulk_load(st + L.uqr, src + (size_t)(16 * g0) * K2S_LDU, (unsigned)ROWS * row_bytes, sfull + si);
+                bulk_load(st + L.uqc, src + (size_t)(cb * K2_CWARPS) * K2S_LDU, (unsigned)K2_CWARPS * row_bytes, sfull + si);
+                bulk_load(st + L.trig, sa.trig + ((size_t)ac * nck + kc) * K2S_TRIG_TILE, (unsigned)K2S_TRIG_TILE * 8u, sfull + si);
             }
-            if (lane == 0) bulk_load(st + L.trig, sa.trig + ((size_t)ac * nck + kc) * K2S_TRIG_TILE, (unsigned)K2S_TRIG_TILE * 8u, sfull + si);
         };
 
         double acc[2][2][GMAX][2][NALT][2];
