@@ -1,29 +1,30 @@
-// wd_k2_dmma.cuh -- the hot kernel: batched d^j(beta) / D^j(alpha,beta,gamma) contraction on the FP64
-// tensor pipe (mma.sync m8n8k4 f64 -> SASS DMMA.8x8x4, the only FP64 tensor path on sm_100a).
+// wd_k2_dmma.cuh -- the hot kernels: batched d^j(beta) / D^j(alpha,beta,gamma) contraction on the FP64
+// tensor pipe (mma.sync m8n8k4 f64 -> SASS DMMA.8x8x4, the only FP64 tensor path on sm_100a), table of the j being
+// computed resident in shared memory (2j <= 223; wd_k2_stream.cuh streams the mu axis beyond).
 //
-//   CTA, persistent over chunks of 16 angles:
-//     real d   : 12 warps, warp-specialised -- 8 COMPUTE warps (two warpgroups, 208 registers after
-//                setmaxnreg.inc) and 4 STORE warps (one warpgroup, 56 registers after setmaxnreg.dec);
-//     complex D: 8 warps that do both jobs (the store needs the per-chunk phase tables).
+//   k2_real_kernel<HALF>  real d.  16 warps, warp-specialised: 8 COMPUTE warps (200 registers after setmaxnreg.inc)
+//                         and 8 STORE warps (56 after setmaxnreg.dec).  Persistent over chunks of 16 angles; the next
+//                         chunk's trig tables are made while the current one is computed; no CTA barrier.
+//   k2_cplx_kernel<HALF>  complex D.  8 warps that do both jobs (the drain multiplies by the per-chunk phase tables).
+//
 //   Shared memory: UQ (all of it, one TMA bulk copy, zero-padded to whole 16-row groups), the mu / w vectors, the
-//   chunk's trig tables Tc/Ts[16][ldt] (w cos(mu beta), w sin(mu beta)), optional phase tables, and one 16 x 64
-//   staging tile + descriptor + full/empty mbarrier pair per compute warp.
+//   trig tables Tc/Ts[16][ldt] (w cos(mu beta), w sin(mu beta); two buffers in the real kernel), the phase tables
+//   (complex), and per compute warp a ring of two 8 x 64 staging slots + descriptors + full/empty mbarriers.
 //   Warp unit = one quadrant column qn  x  up to GMAX groups of 16 quadrant rows  x  16 angles.
 //   MMA roles:  A[8 angles][4 kp] = T(beta, kp) * UQ[qn][kp],  B[4 kp][8 rows] = UQ[row][kp],
 //   C[8 angles][8 rows].  A 16-row group is two tiles -- its even rows and its odd rows -- so that one tile
 //   needs one trig function; a lane then owns 4 consecutive rows of the group.  Angle tile ai holds the
 //   angles of parity ai of the chunk (angle a = 2 r + ai in MMA row r).
-//   Epilogue (compute warp): butterfly P0 +- P1, sign sigma, and for each of the four mirror targets the
-//   16 x span tile is written to the warp's staging buffer (conflict-free 16-byte STS) and handed to a store
-//   warp through the full/empty mbarriers.  Store warp: drains tiles of its two compute warps -- every store
-//   instruction writes 256 contiguous bytes of one output column (partial-sector writes are what the L2 cannot
-//   absorb: direct register stores of the same data ran this kernel at 17-19 ms).
+//   Epilogue: butterfly S = P0 + P1, D = P0 - P1.  S belongs to the mirror pair (i,i'), (ir,i'r), D to (ir,i'),
+//   (i,i'r): each is staged ONCE per angle tile (conflict-free 16-byte STS) and every staged value is written to both
+//   targets of its pair -- an ascending run in one output column, a descending run in the mirror column -- by the
+//   store warp (real d: sign sigma in place, 256 contiguous bytes per store instruction) or by the warp itself
+//   (complex D: conjugate phases, 512 bytes per instruction).  Partial-sector writes are what the L2 cannot absorb:
+//   direct register stores of the same data ran the first version of this kernel at 17-19 ms.
 //
 //   Why warp specialisation (ncu + experiment builds, profiles/): with 8 symmetric warps the drain loop --
-//   ~1100 dependent integer/LDS/STG instructions per unit, ~5 cycles each with only two warps per scheduler --
-//   kept every warp out of its main loop for ~45 % of the time (12.1 ms at cfg-2); without the drain the same
-//   kernel runs in 8.9 ms.  Moving the drain to otherwise idle warps lets the compute warps return to the DMMA
-//   pipe after ~600 instructions.
+//   ~1100 dependent integer/LDS/STG instructions per unit -- kept every warp out of its main loop for ~45 % of the
+//   time (12.1 ms at cfg-2); without the drain the same kernel ran in 8.9 ms.  DESIGN.md section 4 has the history.
 #pragma once
 #include "wd_kernels.cuh"
 
@@ -724,7 +725,7 @@ __global__ void __launch_bounds__(K2_THREADS_REAL, 1) k2_real_kernel(K2Args a)
     rc.full = bars + 2 * warp; rc.empty = bars + 2 * K2_CWARPS + 2 * warp;
     rc.tiles = 0;
     rc.NN = (size_t)p.N * p.N;
-    // hand-off between the two compute warps (w, w+4) of an SM sub-partition: see k2_dmma_kernel
+    // hand-off between the two compute warps (w, w+4) of an SM sub-partition: see k2_cplx_kernel
     cx.krel = a.handoff - 1;
     cx.bar_me = a.handoff ? 2 + warp : 0;
     cx.bar_other = a.handoff ? 2 + (warp ^ 4) : 0;
@@ -763,6 +764,11 @@ __global__ void __launch_bounds__(K2_THREADS_REAL, 1) k2_real_kernel(K2Args a)
         // eight warps then work on adjacent columns, whose output is adjacent in memory.
 #pragma unroll 1
         for (;;) {
+            // The unit index must be grabbed WHILE HOLDING the pair's token.  The token alternates strictly, every loop
+            // iteration consumes it once and passes it on once; grabbing under the token makes "no units left" visible to
+            // the two warps of a pair in alternation order, so that their iteration counts stay compatible.  (Grabbing
+            // before the wait -- to hide the atomic's latency -- lets the second-turn warp win the last unit of a small
+            // item while its partner has already left: its next wait for the token then never ends.  Measured: a hang.)
             if (cx.bar_me) named_bar_sync(cx.bar_me, 64);
             int v = 0;
             if (lane == 0) v = atomicAdd(sCounter + b, 1);

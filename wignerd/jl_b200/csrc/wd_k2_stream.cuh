@@ -1,6 +1,6 @@
 // wd_k2_stream.cuh -- the DMMA contraction for j whose eigenvector table does not fit in shared memory
-// (2j > ~240, up to the supported maximum): same mathematics, warp unit, epilogue and store warps as
-// k2_dmma_kernel (wd_k2_dmma.cuh), but the mu axis is streamed.
+// (2j > 223, up to the supported maximum): same mathematics, warp unit, epilogue and store warps as
+// k2_real_kernel (wd_k2_dmma.cuh), but the mu axis is streamed.
 //
 //   CTA tile = 16 angles x one block of 16*GMAX quadrant rows x 8 quadrant columns (one column per compute warp).
 //   The mu axis is cut into chunks of <= 32 columns per eigenvector class; per chunk a stage of a 4-deep ring in

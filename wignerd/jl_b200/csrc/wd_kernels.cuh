@@ -17,9 +17,10 @@
 //                        which is what LAPACK zheevr -- the reference's eigen!, :161 -- ends in) at the
 //                        analytically known eigenvalues; one thread per eigenvector, all j in one launch.
 //   k2_plain_kernel      FP64-ALU contraction, any j (fallback + on-GPU cross-check).
-//   k2_dmma_kernel       (wd_k2_dmma.cuh) the hot kernel: DMMA.8x8x4 contraction over (angle tile) x (m tile), UQ resident
-//                        in shared memory, in-kernel trig tables, shared-memory staged coalesced stores,
-//                        optional fused exp(-i(m alpha + n gamma)) epilogue (complex D).
+//   k2_real_kernel       (wd_k2_dmma.cuh) the hot kernel: DMMA.8x8x4 contraction over (angle tile) x (m tile), UQ resident
+//                        in shared memory, trig tables made one chunk ahead, store warps writing two mirror targets
+//                        per staged tile; k2_cplx_kernel: the same with a fused exp(-i(m alpha + n gamma)) epilogue.
+//   k2_stream_kernel     (wd_k2_stream.cuh) the same contraction with the mu axis streamed through a TMA-fed ring.
 //   k4_jmn_kernel        single elements (wignerdjmn / wignerDjmn): one warp per tuple.
 #pragma once
 #include <cuda_runtime.h>
