@@ -1,4 +1,4 @@
-# round-end measurement driver (one gpurun call): smoke first (abort on failure), tests, benches, ncu captures
+# round-end validation driver (one gpurun call): smoke first (abort on failure), the whole GPU test-suite, cfg-4, ncu of the streaming kernel
 timeout 120 python __graft_entry__.py --smoke > gpurun_out/smoke_final.log 2>&1; rc=$?; echo "smoke rc=$rc"; tail -1 gpurun_out/smoke_final.log
 if [ $rc -ne 0 ]; then echo "smoke failed: stopping"; exit 1; fi
 timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_final.log 2>&1; rc=$?; echo "pytest rc=$rc"; tail -2 gpurun_out/pytest_gpu_final.log
