@@ -288,10 +288,10 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
     a.p = pl.dev;
     a.alpha = alpha; a.beta = beta; a.gamma = gamma;
     a.nb = nb; a.out = out; a.equator = equator ? 1 : 0;
-    a.nsplit = 1; a.wrap = 0; a.nfull = 0; a.nitems = 0; a.tsplit = 1;
+    a.nsplit = 1; a.nostore = 0; a.nfull = 0; a.nitems = 0; a.tsplit = 1;
     {
-        const char *e = getenv("WD_K2_WRAP");            // kernel-experiment knob: 1 = no store instructions (SM-side time)
-        if (e) a.wrap = strtoull(e, nullptr, 10);
+        const char *e = getenv("WD_K2_NOSTORE");         // kernel-experiment knob: 1 = no store instructions (SM-side time)
+        if (e) a.nostore = atoi(e) != 0;
     }
     {
         // hand-off between the two compute warps of a sub-partition: the partner is released when ~2/3 of the k-steps of a

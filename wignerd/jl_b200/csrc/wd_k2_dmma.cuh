@@ -528,7 +528,7 @@ __device__ __forceinline__ void k2_emit(const K2Args &a, const K2Ctx &cx, K2RCtx
             d.nrows = ai ? rc.nrows1 : rc.nrows0;
             const int col_a = isD ? cx.N - 1 - ip : ip, col_d = isD ? ip : cx.N - 1 - ip;
             d.dib_a = (row_a - col_a) & 3; d.dib_d = (row_d - col_d) & 3;
-            d.kind = a.wrap == 1 ? 0 : (isD ? (K2_TILE_DESC | (both ? K2_TILE_ASC : 0)) : (K2_TILE_ASC | (both ? K2_TILE_DESC : 0)));
+            d.kind = a.nostore ? 0 : (isD ? (K2_TILE_DESC | (both ? K2_TILE_ASC : 0)) : (K2_TILE_ASC | (both ? K2_TILE_DESC : 0)));
             rc.desc[slot] = d;
         }
         // the lane owns rows 16g+4c .. 16g+4c+3 of the unit: (even tile, odd tile) interleaved

@@ -149,7 +149,7 @@ struct K2Args {
     int nsplit;                           // complex-D DMMA kernel: CTAs per chunk (small batches)
     long long nfull, nitems;              // real-d DMMA kernel: whole-chunk items, all items (k2_item)
     int tsplit;                           // real-d DMMA kernel: CTAs per chunk of the last partial wave
-    unsigned long long wrap;              // experiment knob (WD_K2_WRAP=1): run the real-d DMMA kernel without its store instructions
+    int nostore;                          // experiment knob (WD_K2_NOSTORE=1): run the real-d DMMA kernels without their store instructions
 };
 
 template <bool CPLX>
