@@ -309,7 +309,7 @@ def main():
     h_out = None
     while h_out is None:
         try:
-            h_out = torch.empty((ne, N, N), dtype=torch.complex128 if cplx else torch.float64).pin_memory()
+            h_out = torch.empty((ne, N, N), dtype=torch.complex128 if cplx else torch.float64, pin_memory=True)
         except RuntimeError:
             if ne <= 16384:
                 raise
