@@ -247,6 +247,10 @@ int launch_stream(wd_handle_t h, const Plan &cpl, const K2Args &a)
         const long long total = (long long)(nck0 + nck1) * a.p.Q * K2S_KC;
         k2s_table_kernel<<<(int)std::min<long long>((total + 255) / 256, (long long)h->num_sms * 8), 256, 0, h->stream>>>(a.p, buf, qpad, nck0, nck1);
         h->launches++;
+        // one-time per plan: finish before the pointer is published (the handle's stream may be changed between calls)
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { cudaFree(buf); return fail(WD_ERR_CUDA, "building the chunk-major table of 2j = %d failed: %s", a.p.twoj, cudaGetErrorString(e)); }
         pl.uqc = buf; pl.uqc_qpad = qpad;
     }
     const K2SSmem L = k2s_smem_layout(HALF);
