@@ -117,6 +117,11 @@ int wd_Djmn_batch(wd_handle_t h, const int32_t *twoj, const int32_t *twom, const
  * kernel, 2 = force the resident DMMA kernel (fails if the table of j does not fit in shared
  * memory: 2j > 223), 3 = force the streaming DMMA kernel (real d). */
 int wd_set_variant(wd_handle_t h, int variant);
+/* dynamic shared memory (bytes) that the DMMA kernels need for a given 2j -- kernel 0: resident real-d kernel,
+ * 1: resident complex-D kernel, 2: streaming kernel (independent of j).  A resident kernel is used when this fits
+ * the device's opt-in limit (232448 bytes on sm_100a: 2j <= 223).  Pure host arithmetic, no GPU needed; -1 on bad
+ * arguments. */
+int64_t wd_k2_shared_bytes(int32_t twoj, int kernel);
 /* FP64 micro-benchmarks used to calibrate the roofline (bench.py): returns TFLOP/s of a
  * register-resident DMMA.8x8x4 (kind 0) or DFMA (kind 1) loop over the whole chip. */
 int wd_fp64_peak(wd_handle_t h, int kind, int iters, double *tflops);

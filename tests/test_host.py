@@ -39,6 +39,19 @@ def test_exports_every_declared_symbol():
         assert hasattr(L, sym), sym
 
 
+def test_resident_kernel_range():
+    """shared-memory budget of the DMMA kernels (pure host arithmetic of the library): the benchmark's j = 100 and
+    j = 49.5 must stay in the table-resident kernels; bench.py names the kernel of a config by the same limit"""
+    L = w.load_library()
+    limit = 232448                                      # sm_100a opt-in maximum per CTA (227 KB)
+    fits = lambda twoj, k: 0 < L.wd_k2_shared_bytes(twoj, k) <= limit     # noqa: E731
+    assert fits(200, 0) and fits(99, 1)
+    assert max(t for t in range(0, 400) if fits(t, 0)) == 223
+    assert max(t for t in range(0, 400) if fits(t, 1)) == 223
+    assert fits(1024, 2) and fits(1023, 2)
+    assert L.wd_k2_shared_bytes(-1, 0) == -1 and L.wd_k2_shared_bytes(10, 7) == -1
+
+
 def test_package_path_literal():
     # the package is reachable as ./wignerd.jl_b200/ too (same directory)
     assert os.path.samefile(os.path.join(ROOT, "wignerd.jl_b200"), os.path.join(ROOT, "wignerd", "jl_b200"))

@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "wd_create", "wd_destroy", "wd_last_error", "wd_abi_version", "wd_set_stream", "wd_synchronize",
     "wd_launch_count", "wd_cache_clear", "wd_prepare", "wd_eigvecs", "wd_d_batch", "wd_D_batch",
     "wd_d_matrix", "wd_D_matrix", "wd_d_multi", "wd_djmn_batch", "wd_Djmn_batch", "wd_set_variant",
-    "wd_fp64_peak",
+    "wd_fp64_peak", "wd_k2_shared_bytes",
 ]
 
 
@@ -81,6 +81,8 @@ def load_library():
         L.wd_djmn_batch.argtypes = [vp, vp, vp, vp, vp, i64, ctypes.c_int, vp, ctypes.c_int]
         L.wd_Djmn_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, ctypes.c_int, vp, ctypes.c_int]
         L.wd_set_variant.argtypes = [vp, ctypes.c_int]
+        L.wd_k2_shared_bytes.argtypes = [i32, ctypes.c_int]
+        L.wd_k2_shared_bytes.restype = i64
         L.wd_fp64_peak.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(dbl)]
         _lib = L
         return L

@@ -766,6 +766,19 @@ int wd_Djmn_batch(wd_handle_t h, const int32_t *twoj, const int32_t *twom, const
     return jmn_common(h, twoj, twom, twon, alpha, beta, gamma, n, beta_kind, out, mem, true);
 }
 
+int64_t wd_k2_shared_bytes(int32_t twoj, int kernel)
+{
+    if (twoj < 0 || twoj > kMaxTwoJ) return -1;
+    PlanDev p{};
+    plan_dims(twoj, p);
+    switch (kernel) {
+    case 0: return (int64_t)k2r_smem_layout(p.Q, p.Kp, p.ldu).total * (int64_t)sizeof(double);
+    case 1: return (int64_t)k2_smem_layout(p.Q, p.Kp, p.ldu).total * (int64_t)sizeof(double);
+    case 2: return (int64_t)k2s_smem_layout((twoj & 1) != 0).total * (int64_t)sizeof(double);
+    default: return -1;
+    }
+}
+
 int wd_fp64_peak(wd_handle_t h, int kind, int iters, double *tflops)
 {
     if (!h || !tflops) return fail(WD_ERR_ASSERT, "null argument");
