@@ -1,7 +1,8 @@
 """Model check of the hand-off protocol of the real-d DMMA kernel (wignerd/jl_b200/csrc/wd_k2_dmma.cuh,
 k2_real_kernel): the two compute warps of an SM sub-partition pass ONE token back and forth (named barriers
 bar_me / bar_other), every loop iteration consumes it once and emits it once, and unit indices come from a counter
-shared by all eight warps of the CTA.  The kernel grabs the index WHILE HOLDING the token; grabbing before the
+shared by all eight warps of the CTA; the trig tables of item k+1 are made during item k (trig_ready / trig_free
+mbarriers, 8 arrivals each).  The kernel grabs the index WHILE HOLDING the token; grabbing before the
 wait (which would hide the atomic's latency) deadlocks on small items -- that variant hung the GPU once, and is
 kept here as the negative control.  Pure Python, random interleavings; no GPU, no library."""
 import random
@@ -19,10 +20,23 @@ def simulate(units_per_item, grab_under_token, seed, npairs=4):
     def partner(w):
         return w ^ npairs                    # (w, w + npairs) share a sub-partition
 
+    nitems = len(counters)
+    trig_ready = [0] * (nitems + 1)          # arrivals: the tables of item k are complete at 2 * npairs
+    trig_free = [0] * (nitems + 1)           # arrivals: every warp has finished item k
+
+    def prefetch(kn):                        # this warp's share of the trig tables of item kn (other buffer)
+        while kn >= 2 and trig_free[kn - 2] < nwarps:
+            yield "blocked"
+        trig_ready[kn] += 1
+
     def warp(w):
         if w >= npairs:                      # second-turn warps hand the first turn to their partners
             tokens[partner(w)] += 1
-        for k in range(len(counters)):
+        yield from prefetch(0)
+        for k in range(nitems):
+            while trig_ready[k] < nwarps:    # mbar_wait(trig_ready)
+                yield "blocked"
+            pre = k + 1 >= nitems
             while True:
                 have = None
                 if not grab_under_token:     # negative control: index grabbed before the token wait
@@ -41,21 +55,28 @@ def simulate(units_per_item, grab_under_token, seed, npairs=4):
                     yield "ready"            # rest of the main loop + epilogue
                 else:
                     tokens[partner(w)] += 1  # leaving the item: pass the token on
+                if not pre:                  # after the first unit, or when there is none
+                    yield from prefetch(k + 1)
+                    pre = True
+                if not have:
                     break
+            trig_free[k] += 1
         return
 
     gens = {w: warp(w) for w in range(nwarps)}
     state = {w: "ready" for w in gens}
+    stuck = 0
     while gens:
-        runnable = [w for w in gens if state[w] == "ready" or (state[w] == "blocked" and tokens[w] > 0)]
-        if not runnable:
-            return False
-        w = rng.choice(runnable)
+        w = rng.choice(list(gens))
         try:
             state[w] = next(gens[w])
+            stuck = stuck + 1 if state[w] == "blocked" else 0
         except StopIteration:
             del gens[w]
             del state[w]
+            stuck = 0
+        if stuck > 5000:                     # every remaining warp has been polling without progress
+            return False
     return True
 
 
