@@ -6,7 +6,7 @@ import wignerd.jl_b200 as w
 eng = w.Engine(0)
 nb = 512
 beta = torch.linspace(0.0, np.pi, nb, dtype=torch.float64, device="cuda:0")
-for j in (60, 100, 121, 150, 200, 256, 384, 512):
+for j in (30, 60, 100, 111, 112, 150, 200, 256, 384, 512):
     N = 2 * j + 1
     out = torch.empty((nb, N, N), dtype=torch.float64, device="cuda:0")
     for _ in range(3):

@@ -69,6 +69,10 @@ struct wd_handle_s {
     int *d_flag = nullptr;           // error flag / scratch ints
     bool attr_set_cplx[2] = {false, false};
     bool attr_set_stream[2] = {false, false};
+    // stream-ordered pool for the streaming kernel's per-call trig tables, release threshold "never": with the device's
+    // default pool the memory goes back to the OS at every synchronisation and every call after one pays for a fresh
+    // mapping (0.45 -> 0.27 ms per call at j = 150 on 512 angles).  nullptr: creation failed, the default pool is used.
+    cudaMemPool_t pool = nullptr;
     bool attr_set_real[2] = {false, false};
     // host-path workspace, kept across calls (grow-only): angle vectors and two output slabs + their events
     double *ws_ang = nullptr, *ws_slab[2] = {nullptr, nullptr};
@@ -266,7 +270,8 @@ int launch_stream(wd_handle_t h, const Plan &cpl, const K2Args &a)
     const long long nac = (a.nb + K2_ANG - 1) / K2_ANG;
     const size_t ntrig = (size_t)nac * (sa.nck0 + sa.nck1) * K2S_TRIG_TILE;
     double *trig = nullptr;
-    CU(cudaMallocAsync(&trig, ntrig * sizeof(double), h->stream));
+    if (h->pool) CU(cudaMallocFromPoolAsync(&trig, ntrig * sizeof(double), h->pool, h->stream));
+    else CU(cudaMallocAsync(&trig, ntrig * sizeof(double), h->stream));
     sa.trig = trig;
     const long long work = nac * (sa.nck0 + sa.nck1) * K2_ANG * K2S_KC;
     const int tblocks = (int)std::min<long long>((work + 255) / 256, (long long)h->num_sms * 16);
@@ -559,6 +564,21 @@ int wd_create(int device, wd_handle_t *out)
     CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
     CU(cudaMalloc(&h->d_flag, 4 * sizeof(int)));
+    {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&h->pool, &props) == cudaSuccess) {
+            uint64_t never = UINT64_MAX;
+            cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &never);
+        } else {
+            h->pool = nullptr;
+            cudaGetLastError();                           // not fatal: fall back to the default pool
+        }
+    }
     *out = h;
     return WD_OK;
 }
@@ -577,6 +597,7 @@ int wd_destroy(wd_handle_t h)
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
         if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     }
+    if (h->pool) cudaMemPoolDestroy(h->pool);
     cudaStreamDestroy(h->own_stream);
     cudaStreamDestroy(h->copy_stream);
     delete h;
@@ -611,6 +632,7 @@ int wd_cache_clear(wd_handle_t h)
     for (auto &kv : h->plans) { cudaFree(kv.second.uq); if (kv.second.uqc) cudaFree(kv.second.uqc); }
     h->plans.clear();
     h->table_dirty = true;
+    if (h->pool) cudaMemPoolTrimTo(h->pool, 0);
     return WD_OK;
 }
 
