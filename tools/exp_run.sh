@@ -1,7 +1,9 @@
-# guarded experiment driver: quick parity check first (short timeout), then the streaming-kernel tests and cfg-4
-timeout 90 python tools/quick_check.py > gpurun_out/qc.log 2>&1; rc=$?; echo "quick_check rc=$rc"; tail -5 gpurun_out/qc.log | cut -c1-60
+# guarded experiment driver: quick parity check first (short timeout), then timing of the kernel variants at cfg-2
+timeout 120 python tools/quick_check.py > gpurun_out/qc.log 2>&1; rc=$?; echo "quick_check rc=$rc"; tail -12 gpurun_out/qc.log | cut -c1-100
 if [ $rc -ne 0 ]; then echo "stopping"; exit 1; fi
-timeout 100 python bench.py --config cfg4 --steps 5 --warmup 3 > gpurun_out/b_cfg4.log 2>&1; echo "cfg4 rc=$?"; python -c "
+for v in 0 5 2; do
+  timeout 120 python bench.py --config cfg2 --steps 20 --warmup 3 --variant $v --no-cpu-baseline --e2e-angles 2048 > gpurun_out/b_v$v.log 2>&1; echo "variant $v rc=$?"
+  python -c "
 import json
-l=json.loads(open('gpurun_out/b_cfg4.log').read().strip().splitlines()[-1]); print('cfg4', l['ms_per_step'], l['fp64'])"
-timeout 200 python -m pytest tests -m gpu -x -q -k "streaming or large_j or multi_j or very_large or empty_and_single or device_memory or cache_clear" 2>&1 | tail -3
+l=json.loads(open('gpurun_out/b_v$v.log').read().strip().splitlines()[-1]); print('variant $v', l['ms_per_step'], l['clocks'])"
+done

@@ -309,13 +309,37 @@ class Engine:
             raise AssertionError(f"preallocated Jy matrix must be of size ({twoj + 1}, {twoj + 1})")
 
     # -- batched matrices ---------------------------------------------------------------
+    def _check_device(self, t, what):
+        if not t.is_cuda or t.device.index != self.device:
+            raise AssertionError(f"{what} must live on cuda:{self.device} (this engine's device), got {t.device}")
+
     def _angles(self, x, n=None, like=None):
         if _is_torch(x):
-            if x.dtype.is_floating_point is False or str(x.dtype) != "torch.float64" or not x.is_contiguous():
+            if str(x.dtype) != "torch.float64" or not x.is_contiguous():
                 raise AssertionError("device angle arrays must be contiguous float64 tensors")
+            self._check_device(x, "angle arrays")
             return x, MEM_DEVICE
         a = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel())
         return a, MEM_HOST
+
+    def _check_out(self, out, mem, shape, cplx):
+        """a caller-supplied out= must have exactly the layout the library writes: dtype, element count, contiguity,
+        and the memory space / device of the inputs (a mismatch would be an out-of-bounds or cross-device write)."""
+        n = int(np.prod(shape))
+        if mem == MEM_DEVICE:
+            if not _is_torch(out):
+                raise AssertionError("out= must be a torch tensor when the inputs are device tensors")
+            self._check_device(out, "out=")
+            want = "torch.complex128" if cplx else "torch.float64"
+            if str(out.dtype) != want or not out.is_contiguous() or out.numel() != n:
+                raise AssertionError(f"out= must be a contiguous {want} tensor with {n} elements")
+        else:
+            if not isinstance(out, np.ndarray):
+                raise AssertionError("out= must be a numpy array when the inputs are host arrays")
+            want = np.complex128 if cplx else np.float64
+            if out.dtype != want or not out.flags.c_contiguous or out.size != n or not out.flags.writeable:
+                raise AssertionError(f"out= must be a writable C-contiguous {np.dtype(want).name} array with {n} elements")
+        return out
 
     def wignerd_batch(self, j, betas, out=None):
         """d^j(beta_b) for all b: array ``res[b, j+m, j+n]`` (memory: nb column-major matrices back to
@@ -332,6 +356,7 @@ class Engine:
             self._use_torch_stream(b.device)
         elif out is None:
             out = np.empty((nb, N, N), dtype=np.float64)
+        out = self._check_out(out, mem, (nb, N, N), False).reshape(nb, N, N)
         _check(self._lib.wd_d_batch(self._h, twoj, _ptr(b), nb, _ptr(out), mem))
         self._prepared.add(twoj)
         return out.transpose(1, 2) if mem == MEM_DEVICE else out.transpose(0, 2, 1)
@@ -356,6 +381,7 @@ class Engine:
             self._use_torch_stream(b.device)
         elif out is None:
             out = np.empty((nb, N, N), dtype=np.complex128)
+        out = self._check_out(out, mem, (nb, N, N), True).reshape(nb, N, N)
         _check(self._lib.wd_D_batch(self._h, twoj, _ptr(a), _ptr(b), _ptr(g), nb, _ptr(out), mem))
         self._prepared.add(twoj)
         return out.transpose(1, 2) if mem == MEM_DEVICE else out.transpose(0, 2, 1)
@@ -377,6 +403,12 @@ class Engine:
             self._use_torch_stream(b.device)
         elif out is None:
             out = np.empty(total, dtype=np.float64)
+        if len(offsets) != len(twojs) or (len(offsets) and int(offsets.min()) < 0):
+            raise AssertionError("offsets must hold one non-negative entry per j")
+        n_out = out.numel() if mem == MEM_DEVICE else out.size
+        if n_out < total:
+            raise AssertionError(f"out= has {n_out} elements, the offsets need {total}")
+        out = self._check_out(out, mem, (n_out,), False)
         _check(self._lib.wd_d_multi(self._h, _ptr(twojs), len(twojs), _ptr(b), nb, _ptr(out), _ptr(offsets), mem))
         self._prepared.update(int(t) for t in twojs)
         views = []
@@ -388,12 +420,34 @@ class Engine:
 
     # -- batched single elements ----------------------------------------------------------
     def _tuples(self, js, ms, ns):
-        if _is_torch(js):
-            return js, ms, ns, MEM_DEVICE
+        if _is_torch(js) or _is_torch(ms) or _is_torch(ns):
+            import torch
+            if not (_is_torch(js) and _is_torch(ms) and _is_torch(ns)):
+                raise AssertionError("2j, 2m, 2n must all be device tensors or all host arrays")
+            res = []
+            for t, name in ((js, "2j"), (ms, "2m"), (ns, "2n")):
+                self._check_device(t, name)
+                if t.dtype.is_floating_point or t.dtype == torch.bool:
+                    raise AssertionError(f"{name} must be an integer tensor")
+                # torch integer tensors default to int64: the ABI reads int32
+                res.append(t.to(torch.int32).contiguous().reshape(-1))
+            if not (res[0].numel() == res[1].numel() == res[2].numel()):
+                raise AssertionError("2j, 2m, 2n must have the same length")
+            return res[0], res[1], res[2], MEM_DEVICE
         tj = np.ascontiguousarray(js, dtype=np.int32).ravel()
         tm = np.ascontiguousarray(ms, dtype=np.int32).ravel()
         tn = np.ascontiguousarray(ns, dtype=np.int32).ravel()
+        if not (tj.size == tm.size == tn.size):
+            raise AssertionError("2j, 2m, 2n must have the same length")
         return tj, tm, tn, MEM_HOST
+
+    def _tuple_angles(self, x, n, mem, what):
+        a, mem_a = self._angles(x)
+        if mem_a != mem:
+            raise AssertionError(f"tuples and {what} must live in the same memory space")
+        if (a.numel() if mem == MEM_DEVICE else a.size) != n:
+            raise AssertionError(f"{what} must have one entry per tuple ({n})")
+        return a
 
     def wignerdjmn_batch(self, twoj, twom, twon, betas, beta_kind=GENERIC, out=None):
         """tuples given as 2j, 2m, 2n int32 arrays (so half-integers need no special type)."""
@@ -401,9 +455,9 @@ class Engine:
         n = tj.numel() if mem == MEM_DEVICE else tj.size
         b = None
         if betas is not None:
-            b, mem_b = self._angles(betas)
-            if mem_b != mem:
-                raise AssertionError("tuples and angles must live in the same memory space")
+            b = self._tuple_angles(betas, n, mem, "beta")
+        elif int(beta_kind) == GENERIC:
+            raise AssertionError("beta is required for generic co-latitudes")
         if mem == MEM_DEVICE:
             import torch
             if out is None:
@@ -411,17 +465,20 @@ class Engine:
             self._use_torch_stream(tj.device)
         elif out is None:
             out = np.empty(n, dtype=np.float64)
+        out = self._check_out(out, mem, (n,), False)
         _check(self._lib.wd_djmn_batch(self._h, _ptr(tj), _ptr(tm), _ptr(tn), _ptr(b), n, int(beta_kind), _ptr(out), mem))
         return out
 
     def wignerDjmn_batch(self, twoj, twom, twon, alphas, betas, gammas, beta_kind=GENERIC, out=None):
         tj, tm, tn, mem = self._tuples(twoj, twom, twon)
         n = tj.numel() if mem == MEM_DEVICE else tj.size
-        a, _ = self._angles(alphas)
-        g, _ = self._angles(gammas)
+        a = self._tuple_angles(alphas, n, mem, "alpha")
+        g = self._tuple_angles(gammas, n, mem, "gamma")
         b = None
         if betas is not None:
-            b, _ = self._angles(betas)
+            b = self._tuple_angles(betas, n, mem, "beta")
+        elif int(beta_kind) == GENERIC:
+            raise AssertionError("beta is required for generic co-latitudes")
         if mem == MEM_DEVICE:
             import torch
             if out is None:
@@ -429,6 +486,7 @@ class Engine:
             self._use_torch_stream(tj.device)
         elif out is None:
             out = np.empty(n, dtype=np.complex128)
+        out = self._check_out(out, mem, (n,), True)
         _check(self._lib.wd_Djmn_batch(self._h, _ptr(tj), _ptr(tm), _ptr(tn), _ptr(a), _ptr(b), _ptr(g), n,
                                        int(beta_kind), _ptr(out), mem))
         return out

@@ -7,6 +7,7 @@
 #include "wd_kernels.cuh"
 #include "wd_k2_dmma.cuh"
 #include "wd_k2_stream.cuh"
+#include "wd_k2_col.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -63,10 +64,12 @@ struct wd_handle_s {
     size_t smem_optin = 0;
     int64_t launches = 0;
     int variant = 0;
+    int pairing = 1;                 // beta <-> pi - beta pairing in k2_col_kernel (wd_set_option)
     PlanDev *d_table = nullptr;      // plan table indexed by twoj, for K4
     int table_max = -1;
     bool table_dirty = true;
     int *d_flag = nullptr;           // error flag / scratch ints
+    int *d_present = nullptr;        // [kMaxTwoJ + 2] j-presence flags of a tuple list (jmn path)
     bool attr_set_cplx[2] = {false, false};
     bool attr_set_stream[2] = {false, false};
     // stream-ordered pool for the streaming kernel's per-call trig tables, release threshold "never": with the device's
@@ -74,6 +77,8 @@ struct wd_handle_s {
     // mapping (0.45 -> 0.27 ms per call at j = 150 on 512 angles).  nullptr: creation failed, the default pool is used.
     cudaMemPool_t pool = nullptr;
     bool attr_set_real[2] = {false, false};
+    int *d_pair = nullptr;            // ring of device flags written by k2c_pair_check_kernel (one per call in flight)
+    unsigned pair_idx = 0;
     // host-path workspace, kept across calls (grow-only): angle vectors and two output slabs + their events
     double *ws_ang = nullptr, *ws_slab[2] = {nullptr, nullptr};
     size_t ws_ang_bytes = 0, ws_slab_bytes[2] = {0, 0};
@@ -97,48 +102,41 @@ void plan_dims(int twoj, PlanDev &p)
     p.zskip = (twoj & 1) ? 0 : 1;
 }
 
-// Build the tables for all missing twoj of the list with ONE launch of the batched eigensolver.
-int prepare_locked(wd_handle_t h, const int32_t *list, int nj)
+// One launch of the batched eigensolver for the (missing) twoj values todo[0..n).  Temporaries and half-built plans are
+// released on every error path.
+int prepare_batch(wd_handle_t h, const int *todo, size_t n)
 {
-    std::vector<int> todo;
-    for (int i = 0; i < nj; ++i) {
-        const int tj = list[i];
-        if (tj < 0) return fail(WD_ERR_ASSERT, "j must be >= 0 (got 2j = %d)", tj);
-        if (tj > kMaxTwoJ) return fail(WD_ERR_UNSUPPORTED, "2j = %d exceeds the supported maximum %d", tj, kMaxTwoJ);
-        if (!h->plans.count(tj) && std::find(todo.begin(), todo.end(), tj) == todo.end()) todo.push_back(tj);
-    }
-    if (todo.empty()) return WD_OK;
-    CU(cudaSetDevice(h->device));
-    std::vector<EigJob> jobs(todo.size());
-    std::vector<Plan> fresh(todo.size());
+    std::vector<EigJob> jobs(n);
+    std::vector<Plan> fresh(n);
     size_t scratch_total = 0;
     int maxK = 1;
-    for (size_t t = 0; t < todo.size(); ++t) {
-        Plan &pl = fresh[t];
-        plan_dims(todo[t], pl.dev);
-        scratch_total += 2 * (size_t)pl.dev.N * pl.dev.Q;
-        maxK = std::max(maxK, pl.dev.Q);
+    for (size_t t = 0; t < n; ++t) {
+        plan_dims(todo[t], fresh[t].dev);
+        scratch_total += 2 * (size_t)fresh[t].dev.N * fresh[t].dev.Q;
+        maxK = std::max(maxK, fresh[t].dev.Q);
     }
-    double *scratch = nullptr, *tables = nullptr;
-    // one allocation per plan keeps wd_cache_clear simple; scratch is one block
-    CU(cudaMalloc(&scratch, scratch_total * sizeof(double)));
+    double *scratch = nullptr;
+    EigJob *d_jobs = nullptr;
+    auto cleanup = [&](bool drop_tables) {
+        if (scratch) cudaFree(scratch);
+        if (d_jobs) cudaFree(d_jobs);
+        if (drop_tables) for (auto &pl : fresh) if (pl.uq) cudaFree(pl.uq);
+    };
+    cudaError_t e = cudaMalloc(&scratch, scratch_total * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_jobs, n * sizeof(EigJob));
+    if (e != cudaSuccess) { cleanup(true); return fail(WD_ERR_NOMEM, "cudaMalloc of the eigensolver workspace (%zu bytes) failed: %s", scratch_total * sizeof(double), cudaGetErrorString(e)); }
     size_t off = 0;
-    for (size_t t = 0; t < todo.size(); ++t) {
+    for (size_t t = 0; t < n; ++t) {
         Plan &pl = fresh[t];
         const PlanDev &d = pl.dev;
         const size_t nuq = (size_t)d.Q * d.ldu;
-        cudaError_t e = cudaMalloc(&tables, (nuq + 2 * (size_t)d.Kp) * sizeof(double));
-        if (e != cudaSuccess) {
-            cudaFree(scratch);
-            for (size_t s = 0; s < t; ++s) cudaFree(fresh[s].uq);
-            return fail(WD_ERR_NOMEM, "cudaMalloc of the j tables failed: %s", cudaGetErrorString(e));
-        }
+        double *tables = nullptr;                       // one allocation per plan keeps wd_cache_clear simple
+        e = cudaMalloc(&tables, (nuq + 2 * (size_t)d.Kp) * sizeof(double));
+        if (e != cudaSuccess) { cleanup(true); return fail(WD_ERR_NOMEM, "cudaMalloc of the tables of 2j = %d failed: %s", d.twoj, cudaGetErrorString(e)); }
         pl.uq = tables;
         pl.mu = tables + nuq;
         pl.w = pl.mu + d.Kp;
-        pl.dev.uq = pl.uq;
-        pl.dev.mu = pl.mu;
-        pl.dev.w = pl.w;
+        pl.dev.uq = pl.uq; pl.dev.mu = pl.mu; pl.dev.w = pl.w;
         cudaMemsetAsync(pl.uq, 0, nuq * sizeof(double), h->stream);
         EigJob &jb = jobs[t];
         jb.twoj = d.twoj; jb.N = d.N; jb.K = d.Q; jb.K0p = d.K0p; jb.ldu = d.ldu; jb.Kp = d.Kp;
@@ -146,22 +144,48 @@ int prepare_locked(wd_handle_t h, const int32_t *list, int nj)
         jb.scratch = scratch + off;
         off += 2 * (size_t)d.N * d.Q;
     }
-    EigJob *d_jobs = nullptr;
-    CU(cudaMalloc(&d_jobs, jobs.size() * sizeof(EigJob)));
-    CU(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(EigJob), cudaMemcpyHostToDevice, h->stream));
-    // grid.y is limited to 65535: launch in slices
-    for (size_t j0 = 0; j0 < jobs.size(); j0 += 32768) {
-        const unsigned ny = (unsigned)std::min<size_t>(32768, jobs.size() - j0);
+    e = cudaMemcpyAsync(d_jobs, jobs.data(), n * sizeof(EigJob), cudaMemcpyHostToDevice, h->stream);
+    for (size_t j0 = 0; j0 < n && e == cudaSuccess; j0 += 32768) {      // grid.y is limited to 65535: launch in slices
+        const unsigned ny = (unsigned)std::min<size_t>(32768, n - j0);
         dim3 grid((maxK + 127) / 128, ny);
         k1_eig_kernel<<<grid, 128, 0, h->stream>>>(d_jobs + j0);
         h->launches++;
+        e = cudaGetLastError();
     }
-    CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(h->stream));
-    cudaFree(d_jobs);
-    cudaFree(scratch);
-    for (size_t t = 0; t < todo.size(); ++t) h->plans[todo[t]] = fresh[t];
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { cleanup(true); return fail(WD_ERR_CUDA, "batched eigensolver failed: %s", cudaGetErrorString(e)); }
+    cleanup(false);
+    for (size_t t = 0; t < n; ++t) h->plans[todo[t]] = fresh[t];
     h->table_dirty = true;
+    return WD_OK;
+}
+
+// Build the tables for all missing twoj of the list; one launch of the batched eigensolver per <= 1 GiB of scratch.
+int prepare_locked(wd_handle_t h, const int32_t *list, int nj)
+{
+    std::vector<int> todo;
+    std::vector<char> seen((size_t)kMaxTwoJ + 1, 0);
+    for (int i = 0; i < nj; ++i) {
+        const int tj = list[i];
+        if (tj < 0) return fail(WD_ERR_ASSERT, "j must be >= 0 (got 2j = %d)", tj);
+        if (tj > kMaxTwoJ) return fail(WD_ERR_UNSUPPORTED, "2j = %d exceeds the supported maximum %d", tj, kMaxTwoJ);
+        if (!seen[tj] && !h->plans.count(tj)) { seen[tj] = 1; todo.push_back(tj); }
+    }
+    if (todo.empty()) return WD_OK;
+    CU(cudaSetDevice(h->device));
+    const size_t cap = (size_t)1 << 27;                     // doubles of scratch per launch (1 GiB)
+    size_t i = 0;
+    while (i < todo.size()) {
+        size_t j = i, scratch = 0;
+        while (j < todo.size()) {
+            const size_t need = (size_t)(todo[j] + 1) * (size_t)(todo[j] + 2);     // 2 N Q
+            if (j > i && scratch + need > cap) break;
+            scratch += need; ++j;
+        }
+        const int rc = prepare_batch(h, todo.data() + i, j - i);
+        if (rc) return rc;
+        i = j;
+    }
     return WD_OK;
 }
 
@@ -232,6 +256,75 @@ int launch_real(wd_handle_t h, const K2Args &a, size_t smem)
     k2_real_kernel<HALF><<<grid, K2_THREADS_REAL, smem, h->stream>>>(b);
     h->launches++;
     CU(cudaGetLastError());
+    return WD_OK;
+}
+
+// Column-staged DMMA kernel for real d (k2_col_kernel, wd_k2_col.cuh): the default for tables that fit in shared memory
+constexpr int kPairRing = 64;
+bool col_fits(wd_handle_t h, const PlanDev &p, size_t *bytes)
+{
+    const K2CSmem L = k2c_smem_layout(p.Q, p.Kp, p.ldu, p.N);
+    *bytes = (size_t)L.total * sizeof(double);
+    return k2c_shape_ok(p.twoj) && *bytes <= h->smem_optin;
+}
+
+template <bool HALF, int GC>
+cudaError_t launch_col_gc(const K2CArgs &c, int grid, size_t smem, size_t optin, cudaStream_t st)
+{
+    static thread_local bool attr_set = false;            // per instantiation; setting it again is harmless
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k2_col_kernel<HALF, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    k2_col_kernel<HALF, GC><<<grid, K2C_THREADS, smem, st>>>(c);
+    return cudaGetLastError();
+}
+
+int launch_col(wd_handle_t h, const K2Args &a, size_t smem)
+{
+    K2CArgs c;
+    c.p = a.p; c.beta = a.beta; c.nb = a.nb; c.out = a.out;
+    c.handoff = a.handoff; c.flags = a.nostore ? K2C_FLAG_NOSTORE : 0;
+    c.pair_flag = nullptr;
+    // beta <-> pi - beta pairing: decided on the device, no host round trip.  The mirror matrix is computed
+    // from the trig values of its partner: |beta[b] + beta[nb-1-b] - pi| <= tol bounds the extra error by j * tol = 2e-13.
+    if (a.nb >= 2 * K2C_ANG && h->pairing) {
+        int *flag = h->d_pair + (h->pair_idx++ % kPairRing);
+        const double tol = 2e-13 / (double)std::max(1, a.p.twoj / 2);
+        k2c_pair_check_kernel<<<1, 1024, 0, h->stream>>>(a.beta, a.nb, tol, flag);
+        h->launches++;
+        c.pair_flag = flag;
+    }
+    const long long nch = (a.nb + K2C_ANG - 1) / K2C_ANG;
+    const long long G = h->num_sms;
+    long long items = nch;
+    if (nch < G) items = nch * std::max<long long>(1, std::min<long long>(16, G / nch));
+    const int grid = (int)std::min<long long>(items, G);
+    const int gc = (a.p.Q + 15) >> 4;
+    const size_t optin = h->smem_optin;
+    cudaStream_t st = h->stream;
+    cudaError_t e = cudaErrorInvalidValue;
+    if (a.p.twoj & 1) {
+        switch (gc) {
+        case 1: e = launch_col_gc<true, 1>(c, grid, smem, optin, st); break;
+        case 2: e = launch_col_gc<true, 2>(c, grid, smem, optin, st); break;
+        case 3: e = launch_col_gc<true, 3>(c, grid, smem, optin, st); break;
+        case 4: e = launch_col_gc<true, 4>(c, grid, smem, optin, st); break;
+        }
+    } else {
+        switch (gc) {
+        case 1: e = launch_col_gc<false, 1>(c, grid, smem, optin, st); break;
+        case 2: e = launch_col_gc<false, 2>(c, grid, smem, optin, st); break;
+        case 3: e = launch_col_gc<false, 3>(c, grid, smem, optin, st); break;
+        case 4: e = launch_col_gc<false, 4>(c, grid, smem, optin, st); break;
+        case 5: e = launch_col_gc<false, 5>(c, grid, smem, optin, st); break;
+        case 6: e = launch_col_gc<false, 6>(c, grid, smem, optin, st); break;
+        case 7: e = launch_col_gc<false, 7>(c, grid, smem, optin, st); break;
+        }
+    }
+    h->launches++;
+    CU(e);
     return WD_OK;
 }
 
@@ -319,8 +412,13 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
     if (variant == 2 && !fits) return fail(WD_ERR_UNSUPPORTED, "2j = %d does not fit the DMMA kernel (%zu B of shared memory)", pl.dev.twoj, smem);
     // Equator() requests (single matrices, exact zeros of :230-237) take the plain kernel
     if (variant == 3 && !cplx && !equator) return (pl.dev.twoj & 1) ? launch_stream<true>(h, pl, a) : launch_stream<false>(h, pl, a);
-    const bool use_dmma = !equator && ((variant == 2) || (variant == 0 && fits));
     const bool half = pl.dev.twoj & 1;
+    if (!cplx && !equator && (variant == 0 || variant == 4)) {
+        size_t csm = 0;
+        if (col_fits(h, pl.dev, &csm)) return launch_col(h, a, csm);
+        if (variant == 4) return fail(WD_ERR_UNSUPPORTED, "2j = %d does not fit the column-staged DMMA kernel (%zu B of shared memory)", pl.dev.twoj, csm);
+    }
+    const bool use_dmma = !equator && ((variant == 2) || (variant == 0 && fits));
     if (use_dmma && !cplx) return half ? launch_real<true>(h, a, smem) : launch_real<false>(h, a, smem);
     if (use_dmma) return half ? launch_cplx<true>(h, a, smem) : launch_cplx<false>(h, a, smem);
     // real d for a table that does not fit in shared memory: the streaming DMMA kernel
@@ -426,12 +524,15 @@ __global__ void pole_kernel(double *D, int twoj, int kind, int cplx, double alph
     }
 }
 
-__global__ void maxabs_i32_kernel(const int32_t *v, long long n, int *out)
+// marks present[2j] = 1 for every 2j of the tuple list; present[kMaxTwoJ + 1] collects bit 1 (a negative j) and bit 2 (j too large)
+__global__ void mark_twoj_kernel(const int32_t *v, long long n, int *present, int max_twoj)
 {
-    int m = 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        m = max(m, v[i] < 0 ? 0x7fffffff : v[i]);
-    atomicMax(out, m);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int t = v[i];
+        if (t < 0) atomicOr(present + max_twoj + 1, 1);
+        else if (t > max_twoj) atomicOr(present + max_twoj + 1, 2);
+        else if (present[t] == 0) present[t] = 1;
+    }
 }
 
 int ensure_table(wd_handle_t h, int max_twoj)
@@ -496,16 +597,18 @@ int jmn_common(wd_handle_t h, const int32_t *twoj, const int32_t *twom, const in
         // poles never touch the eigenvectors (src/WignerD.jl:218-228): no tables needed
         int maxtj = -1;
         if (beta_kind == WD_BETA_GENERIC || beta_kind == WD_BETA_EQUATOR) {
+            // only the j values that occur are decomposed and cached, like the reference's Jy_eigen (:163-176)
             cudaMemsetAsync(h->d_flag, 0, 2 * sizeof(int), h->stream);
-            maxabs_i32_kernel<<<std::min<long long>(1024, (n + 255) / 256), 256, 0, h->stream>>>(d_tj, n, h->d_flag + 1);
+            cudaMemsetAsync(h->d_present, 0, (kMaxTwoJ + 2) * sizeof(int), h->stream);
+            mark_twoj_kernel<<<(int)std::min<long long>(1024, (n + 255) / 256), 256, 0, h->stream>>>(d_tj, n, h->d_present, kMaxTwoJ);
             h->launches++;
-            if (cudaMemcpyAsync(hflag, h->d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
-                cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = fail(WD_ERR_CUDA, "max(2j) scan failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
-            maxtj = hflag[1];
-            if (maxtj == 0x7fffffff) { rc = fail(WD_ERR_ASSERT, "j must be >= 0"); break; }
-            if (maxtj > kMaxTwoJ) { rc = fail(WD_ERR_UNSUPPORTED, "2j = %d exceeds the supported maximum %d", maxtj, kMaxTwoJ); break; }
-            std::vector<int32_t> all((size_t)maxtj + 1);
-            for (int i = 0; i <= maxtj; ++i) all[i] = i;
+            std::vector<int> present((size_t)kMaxTwoJ + 2);
+            if (cudaMemcpyAsync(present.data(), h->d_present, present.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+                cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = fail(WD_ERR_CUDA, "scan of the j values failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+            if (present[kMaxTwoJ + 1] & 1) { rc = fail(WD_ERR_ASSERT, "j must be >= 0"); break; }
+            if (present[kMaxTwoJ + 1] & 2) { rc = fail(WD_ERR_UNSUPPORTED, "2j exceeds the supported maximum %d", kMaxTwoJ); break; }
+            std::vector<int32_t> all;
+            for (int i = 0; i <= kMaxTwoJ; ++i) if (present[i]) { all.push_back(i); maxtj = i; }
             rc = prepare_locked(h, all.data(), (int)all.size());
             if (rc) break;
             rc = ensure_table(h, maxtj);
@@ -564,6 +667,9 @@ int wd_create(int device, wd_handle_t *out)
     CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
     CU(cudaMalloc(&h->d_flag, 4 * sizeof(int)));
+    CU(cudaMalloc(&h->d_pair, kPairRing * sizeof(int)));
+    CU(cudaMalloc(&h->d_present, (kMaxTwoJ + 2) * sizeof(int)));
+    CU(cudaMemset(h->d_pair, 0, kPairRing * sizeof(int)));
     {
         cudaMemPoolProps props;
         memset(&props, 0, sizeof(props));
@@ -591,6 +697,8 @@ int wd_destroy(wd_handle_t h)
     for (auto &kv : h->plans) { cudaFree(kv.second.uq); if (kv.second.uqc) cudaFree(kv.second.uqc); }
     if (h->d_table) cudaFree(h->d_table);
     if (h->d_flag) cudaFree(h->d_flag);
+    if (h->d_pair) cudaFree(h->d_pair);
+    if (h->d_present) cudaFree(h->d_present);
     if (h->ws_ang) cudaFree(h->ws_ang);
     for (int i = 0; i < 2; ++i) {
         if (h->ws_slab[i]) cudaFree(h->ws_slab[i]);
@@ -639,8 +747,10 @@ int wd_cache_clear(wd_handle_t h)
 int wd_set_variant(wd_handle_t h, int variant)
 {
     if (!h) return fail(WD_ERR_ASSERT, "null handle");
-    if (variant < 0 || variant > 3) return fail(WD_ERR_ASSERT, "variant must be 0..3");
-    h->variant = variant;
+    if (variant < 0 || variant > 5) return fail(WD_ERR_ASSERT, "variant must be 0..5");
+    std::lock_guard<std::mutex> lk(h->mtx);
+    h->pairing = (variant == 5) ? 0 : 1;                 // 5 = auto without the beta <-> pi - beta pairing
+    h->variant = (variant == 5) ? 0 : variant;
     return WD_OK;
 }
 
