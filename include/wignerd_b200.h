@@ -73,6 +73,25 @@ int64_t wd_launch_count(wd_handle_t h);
 /* drop the cached per-j tables (the reference never frees its Dict) */
 int wd_cache_clear(wd_handle_t h);
 
+/* ---- multi-GPU: the (j, beta) batch shards with no inter-GPU traffic ---- */
+/* One handle over ndev GPUs of this process (devices[i], or 0..ndev-1 when devices is NULL; a device may be
+ * listed twice): one single-device child handle + host worker thread per entry.  wd_d_batch / wd_D_batch /
+ * wd_d_multi / wd_djmn_batch / wd_Djmn_batch on such a handle take HOST buffers (mem = WD_MEM_HOST), cut the
+ * angle (or tuple) batch into contiguous slabs with wd_shard_bounds (16-aligned for matrices) and run the slabs
+ * concurrently; every device builds its own tables (the reference's cache is per Task the same way, :137).
+ * wd_prepare / wd_cache_clear / wd_set_variant / wd_synchronize / wd_tables_load act on every child. */
+int wd_create_multi(int ndev, const int *devices, wd_handle_t *out);
+/* number of devices behind a handle (1 for wd_create handles) and the i-th per-device handle: callers that keep
+ * their data on the devices call the batch entry points on the children with WD_MEM_DEVICE and their own slabs. */
+int wd_multi_size(wd_handle_t h);
+int wd_multi_child(wd_handle_t h, int i, wd_handle_t *child);
+/* [lo, hi) of the slab of n batch items owned by rank of world: slab starts are multiples of align (16 = the
+ * kernels' angle chunk), sizes differ by at most align, the slabs partition [0, n).  Pure host arithmetic. */
+int wd_shard_bounds(int64_t n, int rank, int world, int align, int64_t *lo, int64_t *hi);
+/* optional final gather (never part of the timed hot path): concatenates the per-device slabs src[r]
+ * (bytes[r] bytes each, on child r's device) into dst on child dst_child's device with peer copies. */
+int wd_gather(wd_handle_t h, const void *const *src, const int64_t *bytes, int dst_child, void *dst);
+
 /* ---- spectral setup: replaces coeffi + eigen! + cache, src/WignerD.jl:145-185 ------ */
 /* Build (or find cached) the tables for every 2j in the list, in ONE batched launch of
  * the tridiagonal eigensolver.  Implicitly called by everything below. */
@@ -81,6 +100,13 @@ int wd_prepare(wd_handle_t h, const int32_t *twoj_list, int32_t nj);
  * u_out is N x N column-major on the HOST, u_out[(j+m) + N*k] = u[m, mu_k], mu_k = -j+k.
  * <m|mu>_y = (-i)^m u[m,mu] up to a per-mu phase, which cancels in d.  Debug/parity. */
 int wd_eigvecs(wd_handle_t h, int32_t twoj, double *u_out);
+
+/* Persisted tables (extends the in-memory cache of Jy_eigen, :163-176): wd_tables_save writes every cached
+ * table of the handle to a flat file (header + one record per 2j: dims, UQ, mu, w); wd_tables_load puts the
+ * records of a file into the cache (existing entries are kept), so a cold process skips the eigensolver.
+ * A file written by a different table layout is refused with WD_ERR_ARGUMENT. */
+int wd_tables_save(wd_handle_t h, const char *path);
+int wd_tables_load(wd_handle_t h, const char *path);
 
 /* ---- matrices: replaces wignerd/wignerd! (:266-324) and wignerD/wignerD! (:335-357) -- */
 /* nb generic angles -> nb matrices (see layout above).  beta has nb entries. */
@@ -113,17 +139,24 @@ int wd_Djmn_batch(wd_handle_t h, const int32_t *twoj, const int32_t *twom, const
                   int beta_kind, double *out, int mem);
 
 /* ---- introspection for tests / benches ------------------------------------------- */
-/* kernel variant selection for wd_d_batch/wd_D_batch: 0 = auto, 1 = force the plain FP64-ALU
- * kernel, 2 = force the resident DMMA kernel (fails if the table of j does not fit in shared
- * memory: 2j > 223), 3 = force the streaming DMMA kernel (real d). */
+/* kernel variant selection for wd_d_batch/wd_D_batch: 0 = auto (real d, table resident: angle grids that are
+ * symmetric about pi/2 take the column-staged kernel with beta <-> pi - beta pairing, other grids k2_real_kernel --
+ * decided on the device), 1 = force the plain FP64-ALU kernel, 2 = force the resident DMMA kernels k2_real_kernel /
+ * k2_cplx_kernel, 3 = force the streaming DMMA kernel (real d), 4 = force the column-staged DMMA kernel for every grid
+ * (paired when symmetric; fails if the table of j does not fit), 5 = the column-staged kernel without pairing. */
 int wd_set_variant(wd_handle_t h, int variant);
-/* dynamic shared memory (bytes) that the DMMA kernels need for a given 2j -- kernel 0: resident real-d kernel,
- * 1: resident complex-D kernel, 2: streaming kernel (independent of j).  A resident kernel is used when this fits
- * the device's opt-in limit (232448 bytes on sm_100a: 2j <= 223).  Pure host arithmetic, no GPU needed; -1 on bad
- * arguments. */
+/* host path (mem = WD_MEM_HOST): bytes of output per kernel launch / device-to-host copy (default 512 MiB;
+ * two such slabs are double-buffered on the device). */
+int wd_set_slab_bytes(wd_handle_t h, int64_t bytes);
+/* dynamic shared memory (bytes) that the DMMA kernels need for a given 2j -- kernel 0: round-1 resident real-d
+ * kernel, 1: resident complex-D kernel, 2: streaming kernel (independent of j), 3: column-staged real-d kernel (a
+ * huge value when the shape of j is outside its range).  A resident kernel is used when this fits the device's opt-in
+ * limit (232448 bytes on sm_100a).  Pure host arithmetic, no GPU needed; -1 on bad arguments. */
 int64_t wd_k2_shared_bytes(int32_t twoj, int kernel);
-/* FP64 micro-benchmarks used to calibrate the roofline (bench.py): returns TFLOP/s of a
- * register-resident DMMA.8x8x4 (kind 0) or DFMA (kind 1) loop over the whole chip. */
+/* FP64 micro-benchmarks used to calibrate the rooflines (bench.py): returns TFLOP/s of a
+ * register-resident DMMA.8x8x4 (kind 0) or DFMA (kind 1) loop over the whole chip; kind 2: 1e12 full-range
+ * double sin evaluations per second, kind 3: 1e12 complex rotation steps per second (the denominators of the
+ * single-element kernel, cfg-5). */
 int wd_fp64_peak(wd_handle_t h, int kind, int iters, double *tflops);
 
 #ifdef __cplusplus

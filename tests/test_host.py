@@ -129,3 +129,54 @@ def test_shard_bounds_partition(n, world):
     assert max(sizes) - min(sizes) <= 16 or n < 16 * world
     for lo, hi in edges[:-1]:
         assert lo % 16 == 0 or lo == n
+
+
+def test_shard_arithmetic_native_equals_python():
+    """wd_shard_bounds (what a non-Python host and the multi-GPU handle use) == shard.shard_bounds; slabs partition [0, n)"""
+    rng = np.random.default_rng(5)
+    cases = [(0, 1, 16), (1, 8, 16), (15, 2, 16), (16, 2, 16), (17, 3, 16), (100000, 8, 16), (4096, 8, 16), (10_000_000, 7, 1)]
+    cases += [(int(rng.integers(0, 500000)), int(rng.integers(1, 17)), int(rng.choice([1, 8, 16]))) for _ in range(40)]
+    for n, world, align in cases:
+        prev = 0
+        for r in range(world):
+            lo, hi = w.shard_bounds_native(n, r, world, align)
+            assert (lo, hi) == w.shard_bounds(n, r, world, align)
+            assert lo == prev and lo <= hi and (lo % align == 0 or lo == n)
+            prev = hi
+        assert prev == n
+    L = w.load_library()
+    assert L.wd_shard_bounds(10, 3, 2, 16, None, None) == 2
+    lo, hi = ctypes.c_int64(), ctypes.c_int64()
+    assert L.wd_shard_bounds(10, 3, 2, 16, ctypes.byref(lo), ctypes.byref(hi)) == 2      # rank >= world
+
+
+def test_symmetric_shard_is_closed_under_mirroring():
+    """every rank's angle set is mapped onto itself by b -> n-1-b (the pairing of the contraction kernel needs it) and the
+    ranks partition [0, n)"""
+    for n in (100000, 100001, 4096, 800000, 37, 16, 1):
+        for world in (1, 2, 4, 8):
+            seen = np.zeros(n, dtype=int)
+            for r in range(world):
+                (lo, hi), (blo, bhi) = w.symmetric_shard(n, r, world)
+                idx = np.concatenate([np.arange(lo, hi), np.arange(blo, bhi)])
+                seen[idx] += 1
+                assert np.array_equal(np.sort(n - 1 - idx), np.sort(idx))
+                # the rank's own list (front slab then back slab) is mirror-symmetric position by position
+                assert np.array_equal(idx + idx[::-1], np.full(len(idx), n - 1))
+            assert (seen == 1).all()
+
+
+def test_column_kernel_range_and_new_entry_points_reject_nulls():
+    L = w.load_library()
+    limit = 232448
+    assert 0 < L.wd_k2_shared_bytes(200, 3) <= limit          # the benchmark's j = 100 runs in the column-staged kernel
+    assert 0 < L.wd_k2_shared_bytes(99, 3) <= limit
+    assert L.wd_k2_shared_bytes(4, 3) > limit                 # N < 6: plain kernel
+    assert L.wd_k2_shared_bytes(301, 3) > limit
+    assert L.wd_create_multi(0, None, None) == 2
+    h = ctypes.c_void_p()
+    assert L.wd_create_multi(0, None, ctypes.byref(h)) == 2   # ndev must be >= 1
+    assert L.wd_multi_size(None) == 0
+    assert L.wd_tables_save(None, b"/tmp/x") == 2 and L.wd_tables_load(None, None) == 2
+    assert L.wd_gather(None, None, None, 0, None) == 2
+    assert L.wd_set_slab_bytes(None, 1 << 20) == 2

@@ -9,4 +9,4 @@ from .api import (ABI_SYMBOLS, ArgumentError, CudaError, Engine, Equator, Inexac
                   SpecialCoLatitudes, WignerMatrix, _offsetmatrix, _sincos, default_engine, load_library,
                   twoj_of, wignerD, wignerD_, wignerd, wignerd_, wignerdjmn, wignerDjmn,
                   GENERIC, NORTH, SOUTH, EQUATOR, MEM_HOST, MEM_DEVICE, LIB_PATH)
-from .shard import shard_bounds, gather_slabs  # noqa: F401
+from .shard import shard_bounds, shard_bounds_native, symmetric_shard, gather_slabs  # noqa: F401

@@ -31,7 +31,8 @@ ABI_SYMBOLS = [
     "wd_create", "wd_destroy", "wd_last_error", "wd_abi_version", "wd_set_stream", "wd_synchronize",
     "wd_launch_count", "wd_cache_clear", "wd_prepare", "wd_eigvecs", "wd_d_batch", "wd_D_batch",
     "wd_d_matrix", "wd_D_matrix", "wd_d_multi", "wd_djmn_batch", "wd_Djmn_batch", "wd_set_variant",
-    "wd_fp64_peak", "wd_k2_shared_bytes",
+    "wd_fp64_peak", "wd_k2_shared_bytes", "wd_create_multi", "wd_multi_size", "wd_multi_child", "wd_shard_bounds",
+    "wd_gather", "wd_tables_save", "wd_tables_load", "wd_set_slab_bytes",
 ]
 
 
@@ -84,6 +85,14 @@ def load_library():
         L.wd_k2_shared_bytes.argtypes = [i32, ctypes.c_int]
         L.wd_k2_shared_bytes.restype = i64
         L.wd_fp64_peak.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(dbl)]
+        L.wd_create_multi.argtypes = [ctypes.c_int, vp, ctypes.POINTER(vp)]
+        L.wd_multi_size.argtypes = [vp]
+        L.wd_multi_child.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp)]
+        L.wd_shard_bounds.argtypes = [i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+        L.wd_gather.argtypes = [vp, vp, vp, ctypes.c_int, vp]
+        L.wd_tables_save.argtypes = [vp, ctypes.c_char_p]
+        L.wd_tables_load.argtypes = [vp, ctypes.c_char_p]
+        L.wd_set_slab_bytes.argtypes = [vp, i64]
         _lib = L
         return L
 
@@ -237,13 +246,38 @@ def _ptr(x):
 
 
 class Engine:
-    def __init__(self, device: int = 0):
+    """one wd_handle.  ``Engine(device)``: one GPU.  ``Engine(devices=[0, 1, ...])``: a multi-GPU handle
+    (wd_create_multi) -- the batch methods then take HOST arrays and shard them over the devices."""
+
+    def __init__(self, device: int = 0, devices=None):
         self._lib = load_library()
         h = ctypes.c_void_p()
-        _check(self._lib.wd_create(int(device), ctypes.byref(h)))
+        if devices is not None:
+            devs = np.ascontiguousarray(list(devices), dtype=np.int32)
+            _check(self._lib.wd_create_multi(len(devs), _ptr(devs), ctypes.byref(h)))
+            self.devices = [int(d) for d in devs]
+            device = self.devices[0]
+        else:
+            _check(self._lib.wd_create(int(device), ctypes.byref(h)))
+            self.devices = [int(device)]
         self._h = h
         self.device = int(device)
         self._prepared: set[int] = set()
+
+    @property
+    def is_multi(self) -> bool:
+        return int(self._lib.wd_multi_size(self._h)) > 1 or len(self.devices) > 1
+
+    def tables_save(self, path: str):
+        """persist every cached eigenvector table (wd_tables_save)"""
+        _check(self._lib.wd_tables_save(self._h, os.fsencode(path)))
+
+    def tables_load(self, path: str):
+        """load persisted tables into the cache: a cold process skips the eigensolver (wd_tables_load)"""
+        _check(self._lib.wd_tables_load(self._h, os.fsencode(path)))
+
+    def set_slab_bytes(self, nbytes: int):
+        _check(self._lib.wd_set_slab_bytes(self._h, int(nbytes)))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -310,6 +344,8 @@ class Engine:
 
     # -- batched matrices ---------------------------------------------------------------
     def _check_device(self, t, what):
+        if len(self.devices) > 1:
+            raise AssertionError("a multi-GPU engine takes host (numpy) arrays; device tensors go to per-device engines")
         if not t.is_cuda or t.device.index != self.device:
             raise AssertionError(f"{what} must live on cuda:{self.device} (this engine's device), got {t.device}")
 

@@ -14,9 +14,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace wd;
@@ -46,6 +49,66 @@ int fail(int code, const char *fmt, ...)
 
 constexpr int kMaxTwoJ = 4094;
 
+// [lo, hi) of the contiguous slab of n batch items owned by rank (of world): slab starts are multiples of `align` items (the
+// kernels' angle-chunk size), sizes differ by at most `align`, the slabs partition [0, n) exactly.  Mirrors shard.py.
+void shard_bounds(long long n, int rank, int world, int align, long long *lo, long long *hi)
+{
+    const long long nchunks = (n + align - 1) / align;
+    const long long base = nchunks / world, rem = nchunks % world;
+    const long long lo_c = rank * base + std::min<long long>(rank, rem);
+    const long long hi_c = lo_c + base + (rank < rem ? 1 : 0);
+    *lo = std::min(lo_c * align, n);
+    *hi = std::min(hi_c * align, n);
+}
+
+// A few persistent host threads that copy one block of memory in parallel (pinned bounce buffer -> pageable destination).
+class CopyPool {
+public:
+    explicit CopyPool(int nthreads) : n_(std::max(1, nthreads))
+    {
+        for (int i = 0; i < n_; ++i) th_.emplace_back([this, i] { loop(i); });
+    }
+    ~CopyPool()
+    {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    void copy(void *dst, const void *src, size_t bytes)
+    {
+        if (bytes < ((size_t)1 << 20)) { memcpy(dst, src, bytes); return; }
+        std::unique_lock<std::mutex> lk(m_);
+        dst_ = (char *)dst; src_ = (const char *)src; bytes_ = bytes; left_ = n_; ++gen_;
+        cv_.notify_all();
+        done_.wait(lk, [this] { return left_ == 0; });
+    }
+private:
+    void loop(int i)
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(m_);
+            cv_.wait(lk, [&] { return gen_ != seen; });
+            seen = gen_;
+            if (stop_) return;
+            char *d = dst_; const char *s = src_; const size_t b = bytes_;
+            lk.unlock();
+            const size_t per = ((b / n_) + 4095) & ~(size_t)4095;
+            const size_t lo = std::min(b, per * i), hi = std::min(b, per * (i + 1));
+            if (hi > lo) memcpy(d + lo, s + lo, hi - lo);
+            lk.lock();
+            if (--left_ == 0) done_.notify_one();
+        }
+    }
+    int n_;
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    unsigned long long gen_ = 0;
+    bool stop_ = false;
+    char *dst_ = nullptr; const char *src_ = nullptr; size_t bytes_ = 0; int left_ = 0;
+};
+
 struct Plan {
     PlanDev dev{};
     double *uq = nullptr, *mu = nullptr, *w = nullptr;
@@ -64,7 +127,8 @@ struct wd_handle_s {
     size_t smem_optin = 0;
     int64_t launches = 0;
     int variant = 0;
-    int pairing = 1;                 // beta <-> pi - beta pairing in k2_col_kernel (wd_set_option)
+    int pairing = 1;                 // beta <-> pi - beta pairing in k2_col_kernel (wd_set_variant 5 switches it off)
+    size_t slab_bytes = (size_t)512 << 20;   // host path: output slab per kernel launch / device-to-host copy (wd_set_slab_bytes)
     PlanDev *d_table = nullptr;      // plan table indexed by twoj, for K4
     int table_max = -1;
     bool table_dirty = true;
@@ -83,9 +147,22 @@ struct wd_handle_s {
     double *ws_ang = nullptr, *ws_slab[2] = {nullptr, nullptr};
     size_t ws_ang_bytes = 0, ws_slab_bytes[2] = {0, 0};
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    // pageable host destinations: ring of pinned bounce buffers + host copy threads (created on first use)
+    static constexpr int kBounce = 4;
+    static constexpr size_t kBounceBytes = (size_t)32 << 20;
+    char *bounce[kBounce] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_bounce[kBounce] = {nullptr, nullptr, nullptr, nullptr};
+    CopyPool *pool_copy = nullptr;
+    // scalar calls (one matrix, a handful of tuples): a small device block and its pinned mirror, allocated once
+    static constexpr size_t kSmallBytes = (size_t)4 << 20;
+    char *small_dev = nullptr, *small_host = nullptr;
+    // multi-GPU handle (wd_create_multi): one single-device child handle per entry; the parent owns no device state
+    std::vector<wd_handle_t> children;
 };
 
 namespace {
+
+int for_each_child(wd_handle_t h, const std::function<int(wd_handle_t, int)> &f);
 
 void plan_dims(int twoj, PlanDev &p)
 {
@@ -247,10 +324,12 @@ int launch_real(wd_handle_t h, const K2Args &a, size_t smem)
     b.nfull = (nchunks / G) * G;
     const long long rem = nchunks - b.nfull;
     b.tsplit = rem ? (int)std::max<long long>(1, std::min<long long>(16, G / rem)) : 1;
+#ifdef WD_EXPERIMENT
     {
         const char *e = getenv("WD_K2_TAIL");             // kernel-experiment knob: 0 = never split the last wave
         if (e && atoi(e) == 0 && b.nfull > 0) b.tsplit = 1;
     }
+#endif
     b.nitems = b.nfull + rem * b.tsplit;
     const int grid = (int)std::min<long long>(b.nitems, G);
     k2_real_kernel<HALF><<<grid, K2_THREADS_REAL, smem, h->stream>>>(b);
@@ -281,20 +360,35 @@ cudaError_t launch_col_gc(const K2CArgs &c, int grid, size_t smem, size_t optin,
     return cudaGetLastError();
 }
 
-int launch_col(wd_handle_t h, const K2Args &a, size_t smem)
+// mode 0: the column kernel works only if the device-side pair check finds the grid symmetric (the caller launches
+// k2_real_kernel with skip_flag = *flag_out alongside); 1: column kernel for every grid, paired when symmetric;
+// 2: column kernel, never paired
+int launch_col(wd_handle_t h, const K2Args &a, size_t smem, int mode, const int **flag_out)
 {
     K2CArgs c;
     c.p = a.p; c.beta = a.beta; c.nb = a.nb; c.out = a.out;
-    c.handoff = a.handoff; c.flags = a.nostore ? K2C_FLAG_NOSTORE : 0;
+    c.flags = a.nostore ? K2C_FLAG_NOSTORE : 0;
     c.pair_flag = nullptr;
+    c.require_pair = mode == 0;
+    {
+        // hand-off at ~80 % of the k-steps (cfg-2: 50 % 6.73 ms, 65 % 6.50, 81 % 6.39, 100 % 6.64, off 6.90 ms)
+        const int s0 = a.p.K0p / 4, s1 = a.p.K1p / 4;
+        const int target = (4 * (s0 + s1) + 4) / 5;
+        c.handoff = 1 + (target <= s0 ? target / 2 : 100 + (target - s0) / 2);
+#ifdef WD_EXPERIMENT
+        const char *e = getenv("WD_K2_HANDOFF");
+        if (e) c.handoff = atoi(e);
+#endif
+    }
     // beta <-> pi - beta pairing: decided on the device, no host round trip.  The mirror matrix is computed
     // from the trig values of its partner: |beta[b] + beta[nb-1-b] - pi| <= tol bounds the extra error by j * tol = 2e-13.
-    if (a.nb >= 2 * K2C_ANG && h->pairing) {
+    if (mode != 2) {
         int *flag = h->d_pair + (h->pair_idx++ % kPairRing);
         const double tol = 2e-13 / (double)std::max(1, a.p.twoj / 2);
         k2c_pair_check_kernel<<<1, 1024, 0, h->stream>>>(a.beta, a.nb, tol, flag);
         h->launches++;
         c.pair_flag = flag;
+        if (flag_out) *flag_out = flag;
     }
     const long long nch = (a.nb + K2C_ANG - 1) / K2C_ANG;
     const long long G = h->num_sms;
@@ -356,28 +450,38 @@ int launch_stream(wd_handle_t h, const Plan &cpl, const K2Args &a)
         CU(cudaFuncSetAttribute(k2_stream_kernel<HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
         h->attr_set_stream[HALF] = true;
     }
-    K2SArgs sa;
-    sa.base = a;
-    sa.nck0 = nck0; sa.nck1 = nck1;
-    sa.uqc = pl.uqc; sa.qpad = pl.uqc_qpad;
-    const long long nac = (a.nb + K2_ANG - 1) / K2_ANG;
-    const size_t ntrig = (size_t)nac * (sa.nck0 + sa.nck1) * K2S_TRIG_TILE;
-    double *trig = nullptr;
-    if (h->pool) CU(cudaMallocFromPoolAsync(&trig, ntrig * sizeof(double), h->pool, h->stream));
-    else CU(cudaMallocAsync(&trig, ntrig * sizeof(double), h->stream));
-    sa.trig = trig;
-    const long long work = nac * (sa.nck0 + sa.nck1) * K2_ANG * K2S_KC;
-    const int tblocks = (int)std::min<long long>((work + 255) / 256, (long long)h->num_sms * 16);
-    k2s_trig_kernel<<<tblocks, 256, 0, h->stream>>>(a.p, a.beta, a.nb, trig, sa.nck0, sa.nck1);
-    const int gmax = HALF ? 2 : 4;
-    const int ngroups = (a.p.Q + 15) / 16;
-    const long long ntiles = nac * ((ngroups + gmax - 1) / gmax) * ((a.p.Q + K2_CWARPS - 1) / K2_CWARPS);
-    const int grid = (int)std::min<long long>(ntiles, h->num_sms);
-    k2_stream_kernel<HALF><<<grid, K2_THREADS_REAL, smem, h->stream>>>(sa);
-    h->launches += 2;
-    cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(trig, h->stream);
-    if (e != cudaSuccess) return fail(WD_ERR_CUDA, "streaming kernel launch failed: %s", cudaGetErrorString(e));
+    // the per-call trig table ([angle chunk][mu chunk] tiles of 9 KB) is bounded: batches are cut into angle slabs of at most
+    // 256 MB of table (1.0 GB for j = 512 on 10^5 angles, 10 GB on 10^6, otherwise)
+    const int nck = nck0 + nck1;
+    const long long nac_all = (a.nb + K2_ANG - 1) / K2_ANG;
+    const long long nac_cap = std::max<long long>(1, (((long long)256 << 20) / (long long)sizeof(double)) / ((long long)nck * K2S_TRIG_TILE));
+    for (long long ac0 = 0; ac0 < nac_all; ac0 += nac_cap) {
+        const long long nac = std::min(nac_cap, nac_all - ac0);
+        const long long b0 = ac0 * K2_ANG, cnt = std::min<long long>(nac * K2_ANG, a.nb - b0);
+        K2SArgs sa;
+        sa.base = a;
+        sa.base.beta = a.beta + b0; sa.base.nb = cnt;
+        sa.base.out = a.out + (size_t)b0 * a.p.N * a.p.N;
+        sa.nck0 = nck0; sa.nck1 = nck1;
+        sa.uqc = pl.uqc; sa.qpad = pl.uqc_qpad;
+        const size_t ntrig = (size_t)nac * nck * K2S_TRIG_TILE;
+        double *trig = nullptr;
+        if (h->pool) CU(cudaMallocFromPoolAsync(&trig, ntrig * sizeof(double), h->pool, h->stream));
+        else CU(cudaMallocAsync(&trig, ntrig * sizeof(double), h->stream));
+        sa.trig = trig;
+        const long long work = nac * nck * K2_ANG * K2S_KC;
+        const int tblocks = (int)std::min<long long>((work + 255) / 256, (long long)h->num_sms * 16);
+        k2s_trig_kernel<<<tblocks, 256, 0, h->stream>>>(a.p, sa.base.beta, cnt, trig, sa.nck0, sa.nck1);
+        const int gmax = HALF ? 2 : 4;
+        const int ngroups = (a.p.Q + 15) / 16;
+        const long long ntiles = nac * ((ngroups + gmax - 1) / gmax) * ((a.p.Q + K2_CWARPS - 1) / K2_CWARPS);
+        const int grid = (int)std::min<long long>(ntiles, h->num_sms);
+        k2_stream_kernel<HALF><<<grid, K2_THREADS_REAL, smem, h->stream>>>(sa);
+        h->launches += 2;
+        cudaError_t e = cudaGetLastError();
+        cudaFreeAsync(trig, h->stream);
+        if (e != cudaSuccess) return fail(WD_ERR_CUDA, "streaming kernel launch failed: %s", cudaGetErrorString(e));
+    }
     return WD_OK;
 }
 
@@ -390,11 +494,13 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
     a.p = pl.dev;
     a.alpha = alpha; a.beta = beta; a.gamma = gamma;
     a.nb = nb; a.out = out; a.equator = equator ? 1 : 0;
-    a.nsplit = 1; a.nostore = 0; a.nfull = 0; a.nitems = 0; a.tsplit = 1;
+    a.nsplit = 1; a.nostore = 0; a.nfull = 0; a.nitems = 0; a.tsplit = 1; a.skip_flag = nullptr;
+#ifdef WD_EXPERIMENT
     {
         const char *e = getenv("WD_K2_NOSTORE");         // kernel-experiment knob: 1 = no store instructions (SM-side time)
         if (e) a.nostore = atoi(e) != 0;
     }
+#endif
     {
         // hand-off between the two compute warps of a sub-partition: the partner is released when ~2/3 of the k-steps of a
         // main loop are done (real d, second-generation kernel, cfg-2: release at 50 % 9.43 ms, 58-73 % 9.21-9.24 ms, 81 %
@@ -403,20 +509,35 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
         const int s0 = pl.dev.K0p / 4, s1 = pl.dev.K1p / 4;
         const int target = cplx ? (4 * (s0 + s1) + 4) / 5 : (2 * (s0 + s1) + 1) / 3;
         a.handoff = 1 + (target <= s0 ? target / 2 : 100 + (target - s0) / 2);
+#ifdef WD_EXPERIMENT
         const char *e = getenv("WD_K2_HANDOFF");        // kernel-experiment knob
         if (e) a.handoff = atoi(e);
+#endif
     }
     size_t smem = 0;
     const bool fits = cplx ? cplx_fits(h, pl.dev, &smem) : real_fits(h, pl.dev, &smem);
-    const int variant = h->variant;
+    // variants 4 / 5 select the real-d column kernel only: complex D and Equator requests are dispatched as in auto mode
+    const int variant = ((cplx || equator) && (h->variant == 4 || h->variant == 5)) ? 0 : h->variant;
     if (variant == 2 && !fits) return fail(WD_ERR_UNSUPPORTED, "2j = %d does not fit the DMMA kernel (%zu B of shared memory)", pl.dev.twoj, smem);
     // Equator() requests (single matrices, exact zeros of :230-237) take the plain kernel
     if (variant == 3 && !cplx && !equator) return (pl.dev.twoj & 1) ? launch_stream<true>(h, pl, a) : launch_stream<false>(h, pl, a);
     const bool half = pl.dev.twoj & 1;
-    if (!cplx && !equator && (variant == 0 || variant == 4)) {
+    if (!cplx && !equator && (variant == 0 || variant == 4 || variant == 5)) {
         size_t csm = 0;
-        if (col_fits(h, pl.dev, &csm)) return launch_col(h, a, csm);
-        if (variant == 4) return fail(WD_ERR_UNSUPPORTED, "2j = %d does not fit the column-staged DMMA kernel (%zu B of shared memory)", pl.dev.twoj, csm);
+        const bool cfits = col_fits(h, pl.dev, &csm);
+        if (variant != 0) {
+            if (!cfits) return fail(WD_ERR_UNSUPPORTED, "2j = %d does not fit the column-staged DMMA kernel (%zu B of shared memory)", pl.dev.twoj, csm);
+            return launch_col(h, a, csm, variant == 4 ? 1 : 2, nullptr);
+        }
+        // auto: symmetric grids (beta[b] + beta[nb-1-b] = pi) -> column kernel with pairing, everything else -> k2_real_kernel.
+        // Both are launched; the device-side check lets exactly one of them work (an empty launch costs ~3 us).
+        if (cfits && fits && h->pairing && nb >= 4 * K2C_ANG) {
+            const int *flag = nullptr;
+            int rc = launch_col(h, a, csm, 0, &flag);
+            if (rc) return rc;
+            a.skip_flag = flag;
+            return half ? launch_real<true>(h, a, smem) : launch_real<false>(h, a, smem);
+        }
     }
     const bool use_dmma = !equator && ((variant == 2) || (variant == 0 && fits));
     if (use_dmma && !cplx) return half ? launch_real<true>(h, a, smem) : launch_real<false>(h, a, smem);
@@ -438,6 +559,60 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
         h->launches++;
     }
     CU(cudaGetLastError());
+    return WD_OK;
+}
+
+// pinned (or registered / managed) host memory?  Pageable memory makes cudaMemcpyAsync a staged, synchronous copy.
+bool host_is_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+int ensure_bounce(wd_handle_t h)
+{
+    if (h->pool_copy) return WD_OK;
+    for (int i = 0; i < wd_handle_s::kBounce; ++i) {
+        if (cudaMallocHost((void **)&h->bounce[i], wd_handle_s::kBounceBytes) != cudaSuccess)
+            return fail(WD_ERR_NOMEM, "cudaMallocHost of a %zu-byte bounce buffer failed", wd_handle_s::kBounceBytes);
+        cudaEventCreateWithFlags(&h->ev_bounce[i], cudaEventDisableTiming);
+    }
+    const unsigned hw = std::thread::hardware_concurrency();
+    h->pool_copy = new CopyPool((int)std::max(2u, std::min(8u, hw / 2)));
+    return WD_OK;
+}
+
+// device -> host copy of one finished slab on the copy stream.  Pinned destination: one cudaMemcpyAsync.  Pageable
+// destination: 32 MB pieces through a ring of pinned bounce buffers, each piece moved on by the host copy threads while the
+// next pieces are in flight (a plain cudaMemcpyAsync into pageable memory is staged by the driver through one small buffer
+// and serialises with the host).
+int copy_out(wd_handle_t h, char *dst, const char *src_dev, size_t bytes, bool pinned)
+{
+    if (pinned) {
+        cudaError_t e = cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, h->copy_stream);
+        if (e != cudaSuccess) return fail(WD_ERR_CUDA, "device-to-host copy failed: %s", cudaGetErrorString(e));
+        return WD_OK;
+    }
+    int rc = ensure_bounce(h);
+    if (rc) return rc;
+    constexpr int R = wd_handle_s::kBounce;
+    const size_t P = wd_handle_s::kBounceBytes;
+    const size_t npieces = (bytes + P - 1) / P;
+    size_t issued = 0, drained = 0;
+    while (drained < npieces) {
+        while (issued < npieces && issued - drained < (size_t)R) {
+            const size_t off = issued * P, len = std::min(P, bytes - off);
+            cudaMemcpyAsync(h->bounce[issued % R], src_dev + off, len, cudaMemcpyDeviceToHost, h->copy_stream);
+            cudaEventRecord(h->ev_bounce[issued % R], h->copy_stream);
+            ++issued;
+        }
+        cudaError_t e = cudaEventSynchronize(h->ev_bounce[drained % R]);
+        if (e != cudaSuccess) return fail(WD_ERR_CUDA, "device-to-host copy failed: %s", cudaGetErrorString(e));
+        const size_t off = drained * P, len = std::min(P, bytes - off);
+        h->pool_copy->copy(dst + off, h->bounce[drained % R], len);
+        ++drained;
+    }
     return WD_OK;
 }
 
@@ -465,7 +640,10 @@ int contract_host(wd_handle_t h, const Plan &pl, const double *alpha, const doub
         cudaMemcpyAsync(d_ang + nb, alpha, nb * sizeof(double), cudaMemcpyHostToDevice, h->stream);
         cudaMemcpyAsync(d_ang + 2 * nb, gamma, nb * sizeof(double), cudaMemcpyHostToDevice, h->stream);
     }
-    const size_t slab_bytes_target = (size_t)512 << 20;
+    const size_t total_bytes = (size_t)nb * per * sizeof(double);
+    // small pageable outputs go through the driver's own staging; large ones through the bounce ring
+    const bool pinned = total_bytes < ((size_t)8 << 20) || host_is_pinned(out);
+    const size_t slab_bytes_target = h->slab_bytes;
     long long slab = std::max<long long>(1, (long long)(slab_bytes_target / (per * sizeof(double))));
     slab = std::min(slab, nb);
     if (slab > K2_ANG) slab -= slab % K2_ANG;
@@ -489,8 +667,7 @@ int contract_host(wd_handle_t h, const Plan &pl, const double *alpha, const doub
         if (rc) break;
         cudaEventRecord(h->ev_done[i], h->stream);
         cudaStreamWaitEvent(h->copy_stream, h->ev_done[i], 0);
-        cudaMemcpyAsync(out + (size_t)b0 * per, h->ws_slab[i], (size_t)cnt * per * sizeof(double), cudaMemcpyDeviceToHost,
-                        h->copy_stream);
+        rc = copy_out(h, (char *)(out + (size_t)b0 * per), (const char *)h->ws_slab[i], (size_t)cnt * per * sizeof(double), pinned);
         cudaEventRecord(h->ev_copied[i], h->copy_stream);
     }
     cudaError_t e1 = cudaStreamSynchronize(h->stream), e2 = cudaStreamSynchronize(h->copy_stream);
@@ -561,33 +738,63 @@ int jmn_common(wd_handle_t h, const int32_t *twoj, const int32_t *twom, const in
     if (!twoj || !twom || !twon || !out || (beta_kind == WD_BETA_GENERIC && !beta) || (cplx && (!alpha || !gamma)))
         return fail(WD_ERR_ASSERT, "null pointer argument");
     if (beta_kind < 0 || beta_kind > 3) return fail(WD_ERR_ASSERT, "bad beta_kind %d", beta_kind);
+    if (!h->children.empty()) {
+        if (mem != WD_MEM_HOST) return fail(WD_ERR_UNSUPPORTED, "a multi-GPU handle takes host buffers; for device buffers use the per-device handles (wd_multi_child)");
+        const int R = (int)h->children.size();
+        return for_each_child(h, [=](wd_handle_t c, int r) {
+            long long lo, hi;
+            shard_bounds(n, r, R, 1, &lo, &hi);
+            if (hi <= lo) return (int)WD_OK;
+            return jmn_common(c, twoj + lo, twom + lo, twon + lo, alpha ? alpha + lo : nullptr, beta ? beta + lo : nullptr,
+                              gamma ? gamma + lo : nullptr, hi - lo, beta_kind, out + (size_t)lo * (cplx ? 2 : 1), mem, cplx);
+        });
+    }
     std::lock_guard<std::mutex> lk(h->mtx);
     CU(cudaSetDevice(h->device));
     const int32_t *d_tj = twoj, *d_tm = twom, *d_tn = twon;
     const double *d_a = alpha, *d_b = beta, *d_g = gamma;
     double *d_out = out;
     void *blk = nullptr;
+    char *stage = nullptr;                      // pinned mirror of the device block (small calls): one copy in, one copy out
+    size_t stage_in = 0, stage_out_off = 0;
     const size_t osz = (cplx ? 2 : 1) * sizeof(double) * (size_t)n;
     if (mem == WD_MEM_HOST) {
         const size_t isz = sizeof(int32_t) * (size_t)n, dsz = sizeof(double) * (size_t)n;
         auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };      // every sub-buffer 256-byte aligned
         const size_t total = 3 * al(isz) + 3 * al(dsz) + al(osz);
-        CU(cudaMalloc(&blk, total));
-        char *pch = (char *)blk;
+        char *base;
+        if (total <= wd_handle_s::kSmallBytes) {
+            base = h->small_dev; stage = h->small_host;                    // scalar calls: per-handle workspace
+        } else {
+            CU(cudaMalloc(&blk, total));
+            base = (char *)blk;
+        }
+        char *pch = base;
         double *pb = (double *)pch; pch += al(dsz);
         double *pa = (double *)pch; pch += al(dsz);
         double *pg = (double *)pch; pch += al(dsz);
-        double *po = (double *)pch; pch += al(osz);
         int32_t *pj = (int32_t *)pch; pch += al(isz);
         int32_t *pm = (int32_t *)pch; pch += al(isz);
-        int32_t *pn = (int32_t *)pch;
-        cudaMemcpyAsync(pj, twoj, isz, cudaMemcpyHostToDevice, h->stream);
-        cudaMemcpyAsync(pm, twom, isz, cudaMemcpyHostToDevice, h->stream);
-        cudaMemcpyAsync(pn, twon, isz, cudaMemcpyHostToDevice, h->stream);
-        if (beta) cudaMemcpyAsync(pb, beta, dsz, cudaMemcpyHostToDevice, h->stream);
-        if (cplx) {
-            cudaMemcpyAsync(pa, alpha, dsz, cudaMemcpyHostToDevice, h->stream);
-            cudaMemcpyAsync(pg, gamma, dsz, cudaMemcpyHostToDevice, h->stream);
+        int32_t *pn = (int32_t *)pch; pch += al(isz);
+        double *po = (double *)pch;
+        if (stage) {
+            memcpy(stage + ((char *)pj - base), twoj, isz);
+            memcpy(stage + ((char *)pm - base), twom, isz);
+            memcpy(stage + ((char *)pn - base), twon, isz);
+            if (beta) memcpy(stage + ((char *)pb - base), beta, dsz);
+            if (cplx) { memcpy(stage + ((char *)pa - base), alpha, dsz); memcpy(stage + ((char *)pg - base), gamma, dsz); }
+            stage_in = (size_t)((char *)po - base);
+            stage_out_off = stage_in;
+            cudaMemcpyAsync(base, stage, stage_in, cudaMemcpyHostToDevice, h->stream);
+        } else {
+            cudaMemcpyAsync(pj, twoj, isz, cudaMemcpyHostToDevice, h->stream);
+            cudaMemcpyAsync(pm, twom, isz, cudaMemcpyHostToDevice, h->stream);
+            cudaMemcpyAsync(pn, twon, isz, cudaMemcpyHostToDevice, h->stream);
+            if (beta) cudaMemcpyAsync(pb, beta, dsz, cudaMemcpyHostToDevice, h->stream);
+            if (cplx) {
+                cudaMemcpyAsync(pa, alpha, dsz, cudaMemcpyHostToDevice, h->stream);
+                cudaMemcpyAsync(pg, gamma, dsz, cudaMemcpyHostToDevice, h->stream);
+            }
         }
         d_tj = pj; d_tm = pm; d_tn = pn; d_a = pa; d_b = pb; d_g = pg; d_out = po;
     }
@@ -625,14 +832,35 @@ int jmn_common(wd_handle_t h, const int32_t *twoj, const int32_t *twom, const in
         if (cplx) k4_jmn_kernel<true><<<blocks, 256, 0, h->stream>>>(a);
         else k4_jmn_kernel<false><<<blocks, 256, 0, h->stream>>>(a);
         h->launches++;
-        if (mem == WD_MEM_HOST) cudaMemcpyAsync(out, d_out, osz, cudaMemcpyDeviceToHost, h->stream);
+        if (mem == WD_MEM_HOST) cudaMemcpyAsync(stage ? (void *)(stage + stage_out_off) : (void *)out, d_out, osz, cudaMemcpyDeviceToHost, h->stream);
         cudaMemcpyAsync(hflag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
         cudaError_t e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) { rc = fail(WD_ERR_CUDA, "jmn kernel failed: %s", cudaGetErrorString(e)); break; }
+        if (stage) memcpy(out, stage + stage_out_off, osz);
         if (hflag[0]) rc = fail(WD_ERR_ARGUMENT, "m or n is inconsistent with j for at least one tuple");
     } while (0);
     if (blk) cudaFree(blk);
     return rc;
+}
+
+
+
+// multi-GPU handle: f(child, rank) runs on one host thread per child; the first error (and its message) is returned
+int for_each_child(wd_handle_t h, const std::function<int(wd_handle_t, int)> &f)
+{
+    const int R = (int)h->children.size();
+    std::vector<int> rcs(R, WD_OK);
+    std::vector<std::string> msgs(R);
+    std::vector<std::thread> th;
+    for (int r = 0; r < R; ++r)
+        th.emplace_back([&, r] {
+            rcs[r] = f(h->children[r], r);
+            if (rcs[r]) msgs[r] = g_err;                   // thread-local message of the worker
+        });
+    for (auto &t : th) t.join();
+    for (int r = 0; r < R; ++r)
+        if (rcs[r]) { g_err = "device " + std::to_string(h->children[r]->device) + ": " + msgs[r]; return rcs[r]; }
+    return WD_OK;
 }
 
 }  // namespace
@@ -644,6 +872,34 @@ extern "C" {
 
 const char *wd_last_error(void) { return g_err.c_str(); }
 int wd_abi_version(void) { return 1; }
+
+static void destroy_single(wd_handle_t h)
+{
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto &kv : h->plans) { cudaFree(kv.second.uq); if (kv.second.uqc) cudaFree(kv.second.uqc); }
+    if (h->d_table) cudaFree(h->d_table);
+    if (h->d_flag) cudaFree(h->d_flag);
+    if (h->d_pair) cudaFree(h->d_pair);
+    if (h->d_present) cudaFree(h->d_present);
+    if (h->ws_ang) cudaFree(h->ws_ang);
+    if (h->small_dev) cudaFree(h->small_dev);
+    if (h->small_host) cudaFreeHost(h->small_host);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ws_slab[i]) cudaFree(h->ws_slab[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+        if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    }
+    for (int i = 0; i < wd_handle_s::kBounce; ++i) {
+        if (h->bounce[i]) cudaFreeHost(h->bounce[i]);
+        if (h->ev_bounce[i]) cudaEventDestroy(h->ev_bounce[i]);
+    }
+    delete h->pool_copy;
+    if (h->pool) cudaMemPoolDestroy(h->pool);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    delete h;
+}
 
 int wd_create(int device, wd_handle_t *out)
 {
@@ -663,13 +919,20 @@ int wd_create(int device, wd_handle_t *out)
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
-    CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    // a failure below releases what has been built so far
+    e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     h->stream = h->own_stream;
-    CU(cudaMalloc(&h->d_flag, 4 * sizeof(int)));
-    CU(cudaMalloc(&h->d_pair, kPairRing * sizeof(int)));
-    CU(cudaMalloc(&h->d_present, (kMaxTwoJ + 2) * sizeof(int)));
-    CU(cudaMemset(h->d_pair, 0, kPairRing * sizeof(int)));
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_flag, 4 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_pair, kPairRing * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_present, (kMaxTwoJ + 2) * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(h->d_pair, 0, kPairRing * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->small_dev, wd_handle_s::kSmallBytes);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&h->small_host, wd_handle_s::kSmallBytes);
+    if (e != cudaSuccess) {
+        destroy_single(h);
+        return fail(e == cudaErrorMemoryAllocation ? WD_ERR_NOMEM : WD_ERR_CUDA, "wd_create: %s", cudaGetErrorString(e));
+    }
     {
         cudaMemPoolProps props;
         memset(&props, 0, sizeof(props));
@@ -689,32 +952,65 @@ int wd_create(int device, wd_handle_t *out)
     return WD_OK;
 }
 
+int wd_create_multi(int ndev, const int *devices, wd_handle_t *out)
+{
+    if (!out) return fail(WD_ERR_ASSERT, "null output pointer");
+    *out = nullptr;
+    if (ndev < 1 || ndev > 64) return fail(WD_ERR_ASSERT, "ndev must be 1..64 (got %d)", ndev);
+    wd_handle_t h = new wd_handle_s;
+    for (int i = 0; i < ndev; ++i) {
+        wd_handle_t c = nullptr;
+        const int rc = wd_create(devices ? devices[i] : i, &c);          // devices == NULL: 0 .. ndev-1; a device may repeat
+        if (rc) {
+            for (wd_handle_t d : h->children) destroy_single(d);
+            delete h;
+            return rc;
+        }
+        h->children.push_back(c);
+    }
+    h->device = h->children[0]->device;
+    *out = h;
+    return WD_OK;
+}
+
+int wd_multi_size(wd_handle_t h) { return h ? (h->children.empty() ? 1 : (int)h->children.size()) : 0; }
+
+int wd_multi_child(wd_handle_t h, int i, wd_handle_t *child)
+{
+    if (!h || !child) return fail(WD_ERR_ASSERT, "null argument");
+    if (h->children.empty()) { if (i != 0) return fail(WD_ERR_ASSERT, "child %d of a single-device handle", i); *child = h; return WD_OK; }
+    if (i < 0 || i >= (int)h->children.size()) return fail(WD_ERR_ASSERT, "child %d out of range (0..%zu)", i, h->children.size() - 1);
+    *child = h->children[i];
+    return WD_OK;
+}
+
+int wd_shard_bounds(int64_t n, int rank, int world, int align, int64_t *lo, int64_t *hi)
+{
+    if (!lo || !hi) return fail(WD_ERR_ASSERT, "null argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(WD_ERR_ASSERT, "bad rank/world %d/%d", rank, world);
+    if (n < 0 || align < 1) return fail(WD_ERR_ASSERT, "negative batch size or bad alignment");
+    long long a, b;
+    shard_bounds(n, rank, world, align, &a, &b);
+    *lo = a; *hi = b;
+    return WD_OK;
+}
+
 int wd_destroy(wd_handle_t h)
 {
     if (!h) return WD_OK;
-    cudaSetDevice(h->device);
-    cudaDeviceSynchronize();
-    for (auto &kv : h->plans) { cudaFree(kv.second.uq); if (kv.second.uqc) cudaFree(kv.second.uqc); }
-    if (h->d_table) cudaFree(h->d_table);
-    if (h->d_flag) cudaFree(h->d_flag);
-    if (h->d_pair) cudaFree(h->d_pair);
-    if (h->d_present) cudaFree(h->d_present);
-    if (h->ws_ang) cudaFree(h->ws_ang);
-    for (int i = 0; i < 2; ++i) {
-        if (h->ws_slab[i]) cudaFree(h->ws_slab[i]);
-        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
-        if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    if (!h->children.empty()) {
+        for (wd_handle_t c : h->children) destroy_single(c);
+        delete h;
+        return WD_OK;
     }
-    if (h->pool) cudaMemPoolDestroy(h->pool);
-    cudaStreamDestroy(h->own_stream);
-    cudaStreamDestroy(h->copy_stream);
-    delete h;
+    destroy_single(h);
     return WD_OK;
 }
 
 int wd_set_stream(wd_handle_t h, void *s)
 {
     if (!h) return fail(WD_ERR_ASSERT, "null handle");
+    if (!h->children.empty()) return fail(WD_ERR_UNSUPPORTED, "a multi-GPU handle has one stream per device: use wd_multi_child");
     std::lock_guard<std::mutex> lk(h->mtx);
     h->stream = s ? (cudaStream_t)s : h->own_stream;
     return WD_OK;
@@ -723,17 +1019,26 @@ int wd_set_stream(wd_handle_t h, void *s)
 int wd_synchronize(wd_handle_t h)
 {
     if (!h) return fail(WD_ERR_ASSERT, "null handle");
+    if (!h->children.empty()) return for_each_child(h, [](wd_handle_t c, int) { return wd_synchronize(c); });
+    std::lock_guard<std::mutex> lk(h->mtx);
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaStreamSynchronize(h->copy_stream));
     return WD_OK;
 }
 
-int64_t wd_launch_count(wd_handle_t h) { return h ? h->launches : 0; }
+int64_t wd_launch_count(wd_handle_t h)
+{
+    if (!h) return 0;
+    if (!h->children.empty()) { int64_t n = 0; for (wd_handle_t c : h->children) n += wd_launch_count(c); return n; }
+    std::lock_guard<std::mutex> lk(h->mtx);
+    return h->launches;
+}
 
 int wd_cache_clear(wd_handle_t h)
 {
     if (!h) return fail(WD_ERR_ASSERT, "null handle");
+    if (!h->children.empty()) return for_each_child(h, [](wd_handle_t c, int) { return wd_cache_clear(c); });
     std::lock_guard<std::mutex> lk(h->mtx);
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
@@ -748,9 +1053,9 @@ int wd_set_variant(wd_handle_t h, int variant)
 {
     if (!h) return fail(WD_ERR_ASSERT, "null handle");
     if (variant < 0 || variant > 5) return fail(WD_ERR_ASSERT, "variant must be 0..5");
+    if (!h->children.empty()) return for_each_child(h, [variant](wd_handle_t c, int) { return wd_set_variant(c, variant); });
     std::lock_guard<std::mutex> lk(h->mtx);
-    h->pairing = (variant == 5) ? 0 : 1;                 // 5 = auto without the beta <-> pi - beta pairing
-    h->variant = (variant == 5) ? 0 : variant;
+    h->variant = variant;
     return WD_OK;
 }
 
@@ -758,6 +1063,7 @@ int wd_prepare(wd_handle_t h, const int32_t *twoj_list, int32_t nj)
 {
     if (!h) return fail(WD_ERR_ASSERT, "null handle");
     if (nj < 0 || (nj > 0 && !twoj_list)) return fail(WD_ERR_ASSERT, "bad j list");
+    if (!h->children.empty()) return for_each_child(h, [=](wd_handle_t c, int) { return wd_prepare(c, twoj_list, nj); });
     std::lock_guard<std::mutex> lk(h->mtx);
     return prepare_locked(h, twoj_list, nj);
 }
@@ -765,6 +1071,7 @@ int wd_prepare(wd_handle_t h, const int32_t *twoj_list, int32_t nj)
 int wd_eigvecs(wd_handle_t h, int32_t twoj, double *u_out)
 {
     if (!h || !u_out) return fail(WD_ERR_ASSERT, "null argument");
+    if (!h->children.empty()) h = h->children[0];
     std::lock_guard<std::mutex> lk(h->mtx);
     const Plan *pl;
     int rc = get_plan(h, twoj, &pl);
@@ -794,6 +1101,19 @@ static int matrices(wd_handle_t h, int32_t twoj, const double *alpha, const doub
     if (nb == 0) return WD_OK;
     if (!beta || !out || (cplx && (!alpha || !gamma))) return fail(WD_ERR_ASSERT, "null pointer argument");
     if (mem != WD_MEM_HOST && mem != WD_MEM_DEVICE) return fail(WD_ERR_ASSERT, "bad mem flag %d", mem);
+    if (!h->children.empty()) {
+        // multi-GPU handle: contiguous 16-aligned slabs of the angle batch per device, no inter-GPU traffic
+        if (mem != WD_MEM_HOST) return fail(WD_ERR_UNSUPPORTED, "a multi-GPU handle takes host buffers; for device buffers use the per-device handles (wd_multi_child) with wd_shard_bounds");
+        if (twoj < 0) return fail(WD_ERR_ASSERT, "j must be >= 0 (got 2j = %d)", twoj);
+        const int R = (int)h->children.size();
+        const size_t per = (size_t)(twoj + 1) * (twoj + 1) * (cplx ? 2 : 1);
+        return for_each_child(h, [=](wd_handle_t c, int r) {
+            long long lo, hi;
+            shard_bounds(nb, r, R, K2_ANG, &lo, &hi);
+            if (hi <= lo) return (int)WD_OK;
+            return matrices(c, twoj, cplx ? alpha + lo : nullptr, beta + lo, cplx ? gamma + lo : nullptr, hi - lo, out + (size_t)lo * per, mem, cplx, equator);
+        });
+    }
     std::lock_guard<std::mutex> lk(h->mtx);
     const Plan *pl;
     int rc = get_plan(h, twoj, &pl);
@@ -817,20 +1137,23 @@ int wd_D_batch(wd_handle_t h, int32_t twoj, const double *alpha, const double *b
 static int pole_matrix(wd_handle_t h, int32_t twoj, int kind, bool cplx, double alpha, double gamma, double *D)
 {
     // the eigen step still runs first in the reference (:306-307); keep the cache behaviour identical
+    if (!h->children.empty()) h = h->children[0];
     std::lock_guard<std::mutex> lk(h->mtx);
     const Plan *pl;
     int rc = get_plan(h, twoj, &pl);
     if (rc) return rc;
     CU(cudaSetDevice(h->device));
     const size_t bytes = (size_t)pl->dev.N * pl->dev.N * (cplx ? 2 : 1) * sizeof(double);
-    double *d_D = nullptr;
-    CU(cudaMalloc(&d_D, bytes));
-    cudaMemcpyAsync(d_D, D, bytes, cudaMemcpyHostToDevice, h->stream);
+    const bool small = bytes <= wd_handle_s::kSmallBytes;
+    double *d_D = small ? (double *)h->small_dev : nullptr;
+    if (!small) CU(cudaMalloc(&d_D, bytes));
+    if (small) { memcpy(h->small_host, D, bytes); cudaMemcpyAsync(d_D, h->small_host, bytes, cudaMemcpyHostToDevice, h->stream); }
+    else cudaMemcpyAsync(d_D, D, bytes, cudaMemcpyHostToDevice, h->stream);
     pole_kernel<<<std::max(1, std::min(64, (pl->dev.N * pl->dev.N + 255) / 256)), 256, 0, h->stream>>>(d_D, twoj, kind, cplx ? 1 : 0, alpha, gamma);
     h->launches++;
-    cudaMemcpyAsync(D, d_D, bytes, cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(small ? (void *)h->small_host : (void *)D, d_D, bytes, cudaMemcpyDeviceToHost, h->stream);
     cudaError_t e = cudaStreamSynchronize(h->stream);
-    cudaFree(d_D);
+    if (small) memcpy(D, h->small_host, bytes); else cudaFree(d_D);
     if (e != cudaSuccess) return fail(WD_ERR_CUDA, "pole fill failed: %s", cudaGetErrorString(e));
     return WD_OK;
 }
@@ -868,6 +1191,21 @@ int wd_d_multi(wd_handle_t h, const int32_t *twoj_list, int32_t nj, const double
     if (nj < 0 || nb < 0) return fail(WD_ERR_ASSERT, "negative count");
     if (nj == 0 || nb == 0) return WD_OK;
     if (!twoj_list || !beta || !out || !offsets) return fail(WD_ERR_ASSERT, "null pointer argument");
+    if (!h->children.empty()) {
+        // every device computes all j for its slab of the angle grid (cfg-4: 4096 / G angles per GPU): matrices [lo, hi) of j_k
+        // live at out + offsets[k] + lo * N_k^2
+        if (mem != WD_MEM_HOST) return fail(WD_ERR_UNSUPPORTED, "a multi-GPU handle takes host buffers; for device buffers use the per-device handles (wd_multi_child) with wd_shard_bounds");
+        for (int k = 0; k < nj; ++k) if (twoj_list[k] < 0) return fail(WD_ERR_ASSERT, "j must be >= 0 (got 2j = %d)", twoj_list[k]);
+        const int R = (int)h->children.size();
+        return for_each_child(h, [=](wd_handle_t c, int r) {
+            long long lo, hi;
+            shard_bounds(nb, r, R, K2_ANG, &lo, &hi);
+            if (hi <= lo) return (int)WD_OK;
+            std::vector<int64_t> off(nj);
+            for (int k = 0; k < nj; ++k) off[k] = offsets[k] + (int64_t)lo * (twoj_list[k] + 1) * (twoj_list[k] + 1);
+            return wd_d_multi(c, twoj_list, nj, beta + lo, hi - lo, out, off.data(), mem);
+        });
+    }
     std::lock_guard<std::mutex> lk(h->mtx);
     int rc = prepare_locked(h, twoj_list, nj);
     if (rc) return rc;
@@ -898,6 +1236,114 @@ int wd_Djmn_batch(wd_handle_t h, const int32_t *twoj, const int32_t *twom, const
     return jmn_common(h, twoj, twom, twon, alpha, beta, gamma, n, beta_kind, out, mem, true);
 }
 
+int wd_set_slab_bytes(wd_handle_t h, int64_t bytes)
+{
+    if (!h) return fail(WD_ERR_ASSERT, "null handle");
+    if (bytes < (1 << 20)) return fail(WD_ERR_ASSERT, "slab size must be at least 1 MiB");
+    if (!h->children.empty()) return for_each_child(h, [bytes](wd_handle_t c, int) { return wd_set_slab_bytes(c, bytes); });
+    std::lock_guard<std::mutex> lk(h->mtx);
+    h->slab_bytes = (size_t)bytes;
+    return WD_OK;
+}
+
+int wd_gather(wd_handle_t h, const void *const *src, const int64_t *bytes, int dst_child, void *dst)
+{
+    // optional final gather of per-device output slabs onto one device (peer copies over NVLink, not part of the hot path)
+    if (!h || !src || !bytes || !dst) return fail(WD_ERR_ASSERT, "null argument");
+    const int R = wd_multi_size(h);
+    if (dst_child < 0 || dst_child >= R) return fail(WD_ERR_ASSERT, "destination child %d out of range", dst_child);
+    wd_handle_t d = h->children.empty() ? h : h->children[dst_child];
+    std::lock_guard<std::mutex> lk(d->mtx);
+    CU(cudaSetDevice(d->device));
+    size_t off = 0;
+    for (int r = 0; r < R; ++r) {
+        wd_handle_t c = h->children.empty() ? h : h->children[r];
+        if (bytes[r] < 0) return fail(WD_ERR_ASSERT, "negative slab size");
+        if (bytes[r] > 0) CU(cudaMemcpyPeerAsync((char *)dst + off, d->device, src[r], c->device, (size_t)bytes[r], d->stream));
+        off += (size_t)bytes[r];
+    }
+    CU(cudaStreamSynchronize(d->stream));
+    return WD_OK;
+}
+
+// ---- persisted eigenvector tables: flat file, one record per 2j -------------------------------
+namespace {
+struct TabHeader { char magic[8]; int32_t version, count; };
+struct TabRecord { int32_t twoj, Q, ldu, Kp; };
+const char kTabMagic[8] = {'W', 'D', 'B', '2', '0', '0', 'T', 'B'};
+}
+
+int wd_tables_save(wd_handle_t h, const char *path)
+{
+    if (!h || !path) return fail(WD_ERR_ASSERT, "null argument");
+    if (!h->children.empty()) h = h->children[0];
+    std::lock_guard<std::mutex> lk(h->mtx);
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(WD_ERR_ARGUMENT, "cannot open %s for writing", path);
+    TabHeader hd;
+    memcpy(hd.magic, kTabMagic, 8);
+    hd.version = 1; hd.count = (int32_t)h->plans.size();
+    bool ok = fwrite(&hd, sizeof hd, 1, f) == 1;
+    std::vector<double> buf;
+    for (auto &kv : h->plans) {
+        const PlanDev &d = kv.second.dev;
+        TabRecord r{d.twoj, d.Q, d.ldu, d.Kp};
+        const size_t n = (size_t)d.Q * d.ldu + 2 * (size_t)d.Kp;       // uq, mu, w are one allocation
+        buf.resize(n);
+        if (cudaMemcpy(buf.data(), kv.second.uq, n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) { ok = false; break; }
+        ok = ok && fwrite(&r, sizeof r, 1, f) == 1 && fwrite(buf.data(), sizeof(double), n, f) == n;
+        if (!ok) break;
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return fail(WD_ERR_CUDA, "writing %s failed", path);
+    return WD_OK;
+}
+
+static int tables_load_single(wd_handle_t h, const char *path)
+{
+    std::lock_guard<std::mutex> lk(h->mtx);
+    CU(cudaSetDevice(h->device));
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(WD_ERR_ARGUMENT, "cannot open %s", path);
+    TabHeader hd;
+    if (fread(&hd, sizeof hd, 1, f) != 1 || memcmp(hd.magic, kTabMagic, 8) != 0 || hd.version != 1 || hd.count < 0) {
+        fclose(f);
+        return fail(WD_ERR_ARGUMENT, "%s is not a table file of this library (version 1)", path);
+    }
+    std::vector<double> buf;
+    int rc = WD_OK;
+    for (int i = 0; i < hd.count && rc == WD_OK; ++i) {
+        TabRecord r;
+        if (fread(&r, sizeof r, 1, f) != 1) { rc = fail(WD_ERR_ARGUMENT, "%s is truncated", path); break; }
+        Plan pl;
+        if (r.twoj < 0 || r.twoj > kMaxTwoJ) { rc = fail(WD_ERR_ARGUMENT, "%s: bad 2j = %d", path, r.twoj); break; }
+        plan_dims(r.twoj, pl.dev);
+        if (r.Q != pl.dev.Q || r.ldu != pl.dev.ldu || r.Kp != pl.dev.Kp) { rc = fail(WD_ERR_ARGUMENT, "%s: layout of 2j = %d does not match this build", path, r.twoj); break; }
+        const size_t nuq = (size_t)r.Q * r.ldu, n = nuq + 2 * (size_t)r.Kp;
+        buf.resize(n);
+        if (fread(buf.data(), sizeof(double), n, f) != n) { rc = fail(WD_ERR_ARGUMENT, "%s is truncated", path); break; }
+        if (h->plans.count(r.twoj)) continue;                      // already cached: keep it
+        double *tables = nullptr;
+        if (cudaMalloc(&tables, n * sizeof(double)) != cudaSuccess) { rc = fail(WD_ERR_NOMEM, "cudaMalloc of the tables of 2j = %d failed", r.twoj); break; }
+        if (cudaMemcpy(tables, buf.data(), n * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(tables); rc = fail(WD_ERR_CUDA, "upload of the tables of 2j = %d failed", r.twoj); break; }
+        pl.uq = tables; pl.mu = tables + nuq; pl.w = pl.mu + r.Kp;
+        pl.dev.uq = pl.uq; pl.dev.mu = pl.mu; pl.dev.w = pl.w;
+        h->plans[r.twoj] = pl;
+        h->table_dirty = true;
+    }
+    fclose(f);
+    return rc;
+}
+
+int wd_tables_load(wd_handle_t h, const char *path)
+{
+    if (!h || !path) return fail(WD_ERR_ASSERT, "null argument");
+    if (!h->children.empty()) return for_each_child(h, [path](wd_handle_t c, int) { return tables_load_single(c, path); });
+    return tables_load_single(h, path);
+}
+
 int64_t wd_k2_shared_bytes(int32_t twoj, int kernel)
 {
     if (twoj < 0 || twoj > kMaxTwoJ) return -1;
@@ -907,6 +1353,7 @@ int64_t wd_k2_shared_bytes(int32_t twoj, int kernel)
     case 0: return (int64_t)k2r_smem_layout(p.Q, p.Kp, p.ldu).total * (int64_t)sizeof(double);
     case 1: return (int64_t)k2_smem_layout(p.Q, p.Kp, p.ldu).total * (int64_t)sizeof(double);
     case 2: return (int64_t)k2s_smem_layout((twoj & 1) != 0).total * (int64_t)sizeof(double);
+    case 3: return k2c_shape_ok(twoj) ? (int64_t)k2c_smem_layout(p.Q, p.Kp, p.ldu, p.N).total * (int64_t)sizeof(double) : ((int64_t)1 << 40);
     default: return -1;
     }
 }
@@ -914,6 +1361,7 @@ int64_t wd_k2_shared_bytes(int32_t twoj, int kernel)
 int wd_fp64_peak(wd_handle_t h, int kind, int iters, double *tflops)
 {
     if (!h || !tflops) return fail(WD_ERR_ASSERT, "null argument");
+    if (!h->children.empty()) h = h->children[0];
     std::lock_guard<std::mutex> lk(h->mtx);
     CU(cudaSetDevice(h->device));
     double *sink = nullptr;
@@ -935,7 +1383,9 @@ int wd_fp64_peak(wd_handle_t h, int kind, int iters, double *tflops)
     cudaFree(sink);
     if (e != cudaSuccess) return fail(WD_ERR_CUDA, "peak kernel failed: %s", cudaGetErrorString(e));
     const double warps = (double)blocks * threads / 32.0;
-    const double flops = (kind == 0) ? warps * iters * 8.0 * 512.0 : (double)blocks * threads * iters * 16.0 * 2.0;
+    // kind 0: DMMA.8x8x4 (512 flops per warp instruction), 1: DFMA, 2 / 3: 1e12 sin evaluations / rotation steps per second
+    const double flops = (kind == 0) ? warps * iters * 8.0 * 512.0 : (kind == 1) ? (double)blocks * threads * iters * 16.0 * 2.0
+                                                                                 : (double)blocks * threads * iters;
     *tflops = flops / (ms * 1e-3) / 1e12;
     return WD_OK;
 }

@@ -27,6 +27,10 @@
 //     The DMMA work per output element halves; the kernel becomes HBM-write bound.
 //   * trig tables of the next item are made during the current one (as in k2_real_kernel); pair hand-off between the
 //     two warps of an SM sub-partition as before.
+//   Measured at cfg-2 (j = 100, 10^5 angles, one B200): symmetric grid 6.4 ms (k2_real_kernel: 9.1-9.25 ms) = 5.0 TB/s of
+//   output; generic grid 9.5 ms -- the 8-angle unit re-reads the A operand twice as often and every warp pays for its own
+//   stores, so generic grids stay with k2_real_kernel (9.1 ms): the host launches both kernels and the device-side
+//   pair check decides which of the two does the work (K2CArgs::require_pair / K2Args::skip_flag).
 #pragma once
 #include "wd_k2_dmma.cuh"
 
@@ -47,6 +51,7 @@ struct K2CArgs {
     const int *pair_flag;     // device flag of k2c_pair_check_kernel (1: b <-> nb-1-b are mirror angles); nullptr = unpaired
     int handoff;              // see K2Args::handoff
     int flags;
+    int require_pair;         // 1: do nothing unless the grid is paired (the unpaired batch goes to k2_real_kernel, launched alongside)
 };
 
 struct K2CSmem {                // offsets in doubles, identical on host and device
@@ -117,7 +122,7 @@ struct K2CWarp {                // per-warp state of the store path
     unsigned long long ebase;   // out / 8
     unsigned long long NN;
     long long nb, H, f0;        // batch size, number of front angles (paired) or nb, first front angle of the item
-    int na;                     // front angles of the item (1..8)
+    int na, nvB;                // front angles of the item (1..8); how many of them have a mirror matrix to write (paired)
     int paired;
     int N, Q, i0, zskip, rs, slot;
     int lane, r, c;
@@ -133,12 +138,6 @@ __device__ __forceinline__ unsigned long long k2c_e0(const K2CWarp &ws, const bo
     const long long b = back ? ws.nb - 1 - (ws.f0 + x) : ws.f0 + x;
     return ws.ebase + (unsigned long long)b * ws.NN + (unsigned long long)(col * ws.N);
 }
-__device__ __forceinline__ bool k2c_valid(const K2CWarp &ws, const bool back, const int x)
-{
-    if (x >= ws.na) return false;
-    return !back || (ws.paired && ws.nb - 1 - (ws.f0 + x) >= ws.H);
-}
-
 // One staging step = one STRETCH (half a column: its ascending part, rows i0 .. N-1 <- quadrant rows q = 0 .. Q-1, or its
 // descending part, rows i0-1 .. 0 <- q = zskip .. Q-1) of one target column, for the 8 angles of the item.  Every lane
 // writes its 4 consecutive quadrant rows per 16-row group, sign applied, into the staging row of its angle (laid out in
@@ -147,13 +146,19 @@ __device__ __forceinline__ bool k2c_valid(const K2CWarp &ws, const bool back, co
 // other in memory order (chain_asc: ascending addresses), so only whole sectors are ever stored -- except at the two ends
 // of the warp's column block.
 //   v: the butterfly result that feeds this part; colsig: the column whose sigma applies (the front matrix's column).
+struct K2CVal {                 // a butterfly result held as (lo, hi) words: the sign of a target is XORed into a copy of hi
+    unsigned lo, hi;
+};
+
 template <bool DESCROWS, int GC>
-__device__ __forceinline__ void k2c_stage(K2CWarp &ws, const double (&v)[GC][2][2], const bool back,
+__device__ __forceinline__ void k2c_stage(K2CWarp &ws, const K2CVal (&v)[GC][4], const bool back,
                                           const int col, const int colsig, const int t, const bool chain_asc)
 {
     const int Q = ws.Q, i0 = ws.i0, lane = ws.lane;
     const int row0 = DESCROWS ? 0 : i0, len = DESCROWS ? i0 : Q;
-    // sign masks of the lane's rows jj = 0..3 of a group (16 g + 4 c vanish mod 4): sigma(row - colsig) [* (-1)^row for the mirror matrix]
+    // sign masks of the lane's rows jj = 0..3 of a group (16 g + 4 c vanish mod 4): sigma(row - colsig) [* (-1)^row for the
+    // mirror matrix].  (Flipping the values in place, relative to their previous sign, saves a move per element but costs
+    // 30 registers and spills: 7.9 instead of 6.5 ms at cfg-2.)
     unsigned m[4];
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
@@ -174,14 +179,15 @@ __device__ __forceinline__ void k2c_stage(K2CWarp &ws, const double (&v)[GC][2][
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
                 const bool ok = (g < GC - 1 || jj < ws.nvl) && !(g == 0 && jj == 0 && skip0);      // only the last group is partial
-                if (ok) pp[DESCROWS ? -(16 * g + jj) : 16 * g + jj] = flip(v[g][jj & 1][jj >> 1], m[jj]);
+                if (ok) pp[DESCROWS ? -(16 * g + jj) : 16 * g + jj] = __hiloint2double((int)(v[g][jj].hi ^ m[jj]), (int)v[g][jj].lo);
             }
         }
     }
     __syncwarp();
+    const int nv = back ? ws.nvB : ws.na;                             // angles of the item that exist for this target
     if (lane < 3 * K2C_ANG) {                                         // lane -> (angle lane / 3, element lane % 3)
         const int x = lane / 3, e = lane - 3 * x;
-        if (k2c_valid(ws, back, x)) {
+        if (x < nv) {
             const unsigned long long es = k2c_e0(ws, back, col, x) + row0;
             const int ph = (int)(es & 3ull), pe = ph + len;
             double *row = slot + x * ws.rs;
@@ -202,15 +208,16 @@ __device__ __forceinline__ void k2c_stage(K2CWarp &ws, const double (&v)[GC][2][
     }
     fence_async_smem();
     __syncwarp();
-    if (lane < K2C_ANG) {
-        if (k2c_valid(ws, back, lane) && !ws.nostore) {
-            const unsigned long long es = k2c_e0(ws, back, col, lane) + row0;
-            const int ph = (int)(es & 3ull), pe = ph + len;
-            int s0, s1;
-            if (chain_asc) { s0 = (ph > 0 && !have) ? 4 : 0; s1 = pe & ~3; }
-            else           { s0 = ph > 0 ? 4 : 0;            s1 = have ? (pe + 3) & ~3 : pe & ~3; }
-            if (s1 > s0) bulk_store(ws.out + ((es - ph) - ws.ebase) + s0, slot + lane * ws.rs + s0, (unsigned)(s1 - s0) * 8u);
-        }
+    // lane -> angle.  (The compiler serialises the 8 copies -- UBLKCP takes uniform registers: ~11 instructions per copy;
+    // tried and dropped: one lane issuing all copies with shuffled parameters 7.4 ms, plain 16-byte vector stores of the
+    // staged windows instead of the TMA 17.9 ms, against 6.5 ms at cfg-2.)
+    if (lane < nv && !ws.nostore) {
+        const unsigned long long es = k2c_e0(ws, back, col, lane) + row0;
+        const int ph = (int)(es & 3ull), pe = ph + len;
+        int s0, s1;
+        if (chain_asc) { s0 = (ph > 0 && !have) ? 4 : 0; s1 = pe & ~3; }
+        else           { s0 = ph > 0 ? 4 : 0;            s1 = have ? (pe + 3) & ~3 : pe & ~3; }
+        if (s1 > s0) bulk_store(ws.out + ((es - ph) - ws.ebase) + s0, slot + lane * ws.rs + s0, (unsigned)(s1 - s0) * 8u);
     }
     bulk_commit();
     ws.steps++;
@@ -223,7 +230,7 @@ __device__ __forceinline__ void k2c_flush(K2CWarp &ws, const int q_last)
     __syncwarp();
     const int t = ws.lane >> 3, x = ws.lane & 7;
     const bool back = t >= 2, asc = (t == 0 || t == 2);      // targets: 0 front/c0, 1 front/c1, 2 back/c0, 3 back/c1; c0 chains ascend
-    if (((ws.have >> t) & 1u) && k2c_valid(ws, back, x) && !ws.nostore) {
+    if (((ws.have >> t) & 1u) && x < (back ? ws.nvB : ws.na) && !ws.nostore) {
         const int col = asc ? ws.i0 + q_last : ws.Q - 1 - q_last;
         // last stretch of the chain: ascending chains end with the ascending part of the column, descending ones with the descending part
         const int row0 = asc ? ws.i0 : 0, len = asc ? ws.Q : ws.i0;
@@ -304,15 +311,17 @@ __device__ __forceinline__ void k2c_unit(const K2Ctx &cx, K2CWarp &ws, const int
     for (int i = 0; i < 2 * GC * 2 * NALT * 2; ++i) (&acc[0][0][0][0][0])[i] = 0.0;
     k2c_mainloop<HALF, GC>(acc, cx, qn);
     // butterfly: S = P0 + P1 -> (i,i'), (ir,i'r);  D = P0 - P1 -> (ir,i'), (i,i'r)  (half-integer j: D from the other trig function)
-    double vS[GC][2][2], vD[GC][2][2];
+    K2CVal vS[GC][4], vD[GC][4];                        // [group][jj]: the lane's rows 16 g + 4 c + jj, jj = 2 h + eo
 #pragma unroll
     for (int g = 0; g < GC; ++g)
 #pragma unroll
         for (int eo = 0; eo < 2; ++eo)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                vS[g][eo][h] = acc[0][g][eo][0][h] + acc[1][g][eo][0][h];
-                vD[g][eo][h] = acc[0][g][eo][NALT - 1][h] - acc[1][g][eo][NALT - 1][h];
+                const double sv = acc[0][g][eo][0][h] + acc[1][g][eo][0][h];
+                const double dv = acc[0][g][eo][NALT - 1][h] - acc[1][g][eo][NALT - 1][h];
+                vS[g][2 * h + eo].lo = (unsigned)__double2loint(sv); vS[g][2 * h + eo].hi = (unsigned)__double2hiint(sv);
+                vD[g][2 * h + eo].lo = (unsigned)__double2loint(dv); vD[g][2 * h + eo].hi = (unsigned)__double2hiint(dv);
             }
     const int c0 = ws.i0 + qn, c1 = ws.Q - 1 - qn;
     const bool mirror = qn >= ws.zskip;                     // n = 0 mirrors onto itself: no column c1
@@ -352,6 +361,7 @@ __global__ void __launch_bounds__(K2C_THREADS, 1) k2_col_kernel(K2CArgs a)
 
     // items: chunks of 8 (front) angles; paired: only the first half of the batch, every unit also writes the mirror matrices
     const int paired = (a.pair_flag != nullptr && a.nb >= 2) ? *reinterpret_cast<const volatile int *>(a.pair_flag) : 0;
+    if (a.require_pair && !paired) return;
     const long long H = paired ? (a.nb + 1) / 2 : a.nb;
     const long long nch = (H + K2C_ANG - 1) / K2C_ANG, G = gridDim.x;
     const long long nfull = (nch / G) * G, rem = nch - nfull;
@@ -441,6 +451,7 @@ __global__ void __launch_bounds__(K2C_THREADS, 1) k2_col_kernel(K2CArgs a)
         mbar_wait(trig_ready + b, (unsigned)(k >> 1) & 1u);
         cx.sTc = sm + L.trig + b * L.trig_size; cx.sTs = cx.sTc + K2C_ANG * ldt;
         ws.f0 = it.f0; ws.na = it.na;
+        ws.nvB = paired ? (int)max(0LL, min((long long)it.na, a.nb - it.f0 - H)) : 0;
         // this warp's block of columns (rotated from item to item so that the uneven block sizes even out)
         const int ncols = it.q_end - it.q_begin, wslot = (warp + (int)(k & 7)) & 7;
         const int q_lo = it.q_begin + ncols * wslot / K2C_WARPS, q_hi = it.q_begin + ncols * (wslot + 1) / K2C_WARPS;

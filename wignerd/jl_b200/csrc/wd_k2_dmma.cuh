@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(K2_THREADS_CPLX, 1) k2_cplx_kernel(K2Args a)
 {
     constexpr int GMAX = HALF ? 2 : 4;
     constexpr int NC = K2_CWARPS * 32;
-    extern __shared__ __align__(16) double sm[];
+    extern __shared__ __align__(128) double sm[];
     const PlanDev &p = a.p;
     const int Q = p.Q, Kp = p.Kp, ldu = p.ldu;
     const K2Smem L = k2_smem_layout(Q, Kp, ldu);
@@ -669,7 +669,9 @@ __global__ void __launch_bounds__(K2_THREADS_REAL, 1) k2_real_kernel(K2Args a)
     constexpr int GMAX = HALF ? 2 : 4;
     constexpr int NT = K2_THREADS_REAL;
     constexpr int NC = K2_CWARPS * 32;
-    extern __shared__ __align__(16) double sm[];
+    extern __shared__ __align__(128) double sm[];
+    // symmetric angle grids belong to k2_col_kernel (launched alongside): the device-side pair check decides, no host round trip
+    if (a.skip_flag != nullptr && *reinterpret_cast<const volatile int *>(a.skip_flag) != 0) return;
     const PlanDev &p = a.p;
     const int Q = p.Q, Kp = p.Kp, ldu = p.ldu;
     const K2RSmem L = k2r_smem_layout(Q, Kp, ldu);
@@ -803,11 +805,23 @@ __global__ void fp64_peak_kernel(int kind, int iters, double *sink)
 #pragma unroll
             for (int i = 0; i < 8; ++i) dmma(acc[i], x, y);
         }
-    } else {
+    } else if (kind == 1) {
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) { acc[i][0] = fma(acc[i][0], x, y); acc[i][1] = fma(acc[i][1], y, x); }
         }
+    } else {
+        // kind 2: full-range double sin (one evaluation per iteration), arguments spread over [0, 630) = mu * beta at j <= 200;
+        // kind 3: one complex rotation step (4 multiply-adds), the recurrence that replaces most of the evaluations in k4_jmn_kernel
+        double t = 0.1 + (blockIdx.x * blockDim.x + threadIdx.x) * 1e-3, c = 1.0, sn = 0.0;
+        const double cd = cos(0.37), sd = sin(0.37);
+        for (int it = 0; it < iters; ++it) {
+            if (kind == 2) acc[0][0] += sin(t);
+            else { const double c2 = c * cd - sn * sd; sn = fma(sn, cd, c * sd); c = c2; acc[0][0] = fma(c, t, acc[0][0]); }
+            t += 1.618;
+            if (t > 630.0) t -= 630.0;
+        }
+        acc[0][1] += c + sn;
     }
     double s = 0;
 #pragma unroll

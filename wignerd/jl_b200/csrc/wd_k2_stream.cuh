@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(K2_THREADS_REAL, 1) k2_stream_kernel(K2SArgs s
     constexpr int GMAX = HALF ? 2 : 4;
     constexpr int NALT = HALF ? 2 : 1;
     constexpr int ROWS = 16 * GMAX;
-    extern __shared__ __align__(16) double sm[];
+    extern __shared__ __align__(128) double sm[];
     const K2Args &a = sa.base;
     const PlanDev &p = a.p;
     const int Q = p.Q, ldu = p.ldu;

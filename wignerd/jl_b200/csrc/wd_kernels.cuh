@@ -150,6 +150,7 @@ struct K2Args {
     long long nfull, nitems;              // real-d DMMA kernel: whole-chunk items, all items (k2_item)
     int tsplit;                           // real-d DMMA kernel: CTAs per chunk of the last partial wave
     int nostore;                          // experiment knob (WD_K2_NOSTORE=1): run the real-d DMMA kernels without their store instructions
+    const int *skip_flag;                 // k2_real_kernel: device flag of k2c_pair_check_kernel; non-zero = the column kernel has this batch
 };
 
 template <bool CPLX>

@@ -22,6 +22,28 @@ def shard_bounds(n: int, rank: int, world: int, align: int = 16) -> tuple[int, i
     return min(lo_c * align, n), min(hi_c * align, n)
 
 
+def shard_bounds_native(n: int, rank: int, world: int, align: int = 16) -> tuple[int, int]:
+    """the same arithmetic through the C ABI (wd_shard_bounds): what a non-Python host uses"""
+    import ctypes
+    from .api import load_library, _check
+    lo, hi = ctypes.c_int64(), ctypes.c_int64()
+    _check(load_library().wd_shard_bounds(int(n), int(rank), int(world), int(align), ctypes.byref(lo), ctypes.byref(hi)))
+    return lo.value, hi.value
+
+
+def symmetric_shard(n: int, rank: int, world: int, align: int = 16) -> tuple[tuple[int, int], tuple[int, int]]:
+    """A shard that is closed under b -> n-1-b: the rank's slab [lo, hi) of the FIRST half of the batch plus its mirror image
+    [n-hi, n-lo) in the second half.  On angle grids that are symmetric about pi/2 (linspace(0, pi, n)) the rank's own
+    angle list -- front slab followed by back slab -- is then symmetric too, which is what the contraction kernel's
+    beta <-> pi - beta pairing needs.  For odd n the middle element goes to the last rank's front slab."""
+    half = (n + 1) // 2
+    lo, hi = shard_bounds(half, rank, world, align)
+    blo, bhi = n - hi, n - lo
+    if n % 2 == 1 and hi == half:         # the middle element is its own mirror: keep it once
+        blo += 1
+    return (lo, hi), (min(blo, bhi), bhi)
+
+
 def gather_slabs(local, n: int, world: int, group=None, align: int = 16):
     """Optional final gather: every rank contributes its slab ``local`` (first dim = its share of the
     batch) and receives the full batch.  Uses torch.distributed.all_gather on padded slabs (works with
