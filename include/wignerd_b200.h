@@ -127,6 +127,15 @@ int wd_D_matrix(wd_handle_t h, int32_t twoj, double alpha, double beta, int beta
 int wd_d_multi(wd_handle_t h, const int32_t *twoj_list, int32_t nj, const double *beta, int64_t nb,
                double *out, const int64_t *offsets, int mem);
 
+/* ---- fused consumer: rotation of spherical-harmonic coefficients (docs/src/index.md:76-84) ------ */
+/* out[b][l^2 + l + m'] = sum_m D^l_{m m'}(alpha_b, beta_b, gamma_b) alm[b * alm_stride + l^2 + l + m]  for l = 0..lmax,
+ * i.e. what a caller of wignerD(l, alpha, beta, gamma) for every l <= lmax does with the matrices (the reference's cfg-4
+ * use case) -- computed from the eigenvectors directly (two tensor-core GEMMs per l), no D matrix is ever formed.
+ * alm, out: interleaved complex128; alm_stride (in complex elements) = 0 rotates ONE shared coefficient set by all nb
+ * rotations, otherwise >= (lmax+1)^2 (one set per rotation); out holds nb * (lmax+1)^2 complex numbers. */
+int wd_rotate_sh(wd_handle_t h, int32_t lmax, const double *alm, int64_t alm_stride, const double *alpha,
+                 const double *beta, const double *gamma, int64_t nb, double *out, int mem);
+
 /* ---- single elements: replaces WignerD.wignerdjmn (:214-237), wignerDjmn (:245) ------ */
 /* n tuples (twoj[t], twom[t], twon[t], beta[t]) -> out[t].  beta_kind applies to all tuples
  * (beta is ignored for NORTH/SOUTH/EQUATOR).  Tuples with m or n outside -j..j (or of the

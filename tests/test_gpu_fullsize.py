@@ -339,3 +339,83 @@ def test_api_argument_checks(engine):
         engine.wignerd_batch(2, b.float())
     with pytest.raises(AssertionError):
         engine.wignerdjmn_batch(tj.double(), tm, tn, b)
+
+
+# ---- fused consumer: rotation of spherical-harmonic coefficients (docs/src/index.md:76-84) -------------
+def _rotate_ref(lmax, alm, a, b, g, ls=None):
+    """a'_{l m'} = sum_m D^l_{m m'} a_{l m} from the oracle's wignerD, for the l in ls (all by default)"""
+    out = {}
+    for l in (range(lmax + 1) if ls is None else ls):
+        D = cref.wignerD_batch(2 * l, a, b, g) if l > 8 else o.wignerD_batch(l, a, b, g)      # [rot, m, m']
+        al = alm[..., l * l:(l + 1) * (l + 1)]
+        out[l] = np.einsum("bmn,bm->bn", D, np.broadcast_to(al, (len(b), 2 * l + 1)))
+    return out
+
+
+@pytest.mark.parametrize("lmax,nb,shared", [(0, 5, True), (1, 7, False), (8, 33, True), (8, 40, False), (64, 50, True), (64, 19, False)])
+def test_rotate_sh_vs_oracle(engine, lmax, nb, shared):
+    rng = np.random.default_rng(100 + lmax + nb)
+    L2 = (lmax + 1) ** 2
+    alm = (rng.normal(size=(L2,) if shared else (nb, L2)) + 1j * rng.normal(size=(L2,) if shared else (nb, L2))) / np.sqrt(2)
+    a, g = rng.uniform(0, 2 * pi, nb), rng.uniform(0, 2 * pi, nb)
+    b = rng.uniform(0, pi, nb)
+    got = engine.rotate_sh(lmax, alm, a, b, g)
+    assert got.shape == (nb, L2)
+    ref = _rotate_ref(lmax, alm, a, b, g)
+    for l, r in ref.items():
+        assert np.abs(got[:, l * l:(l + 1) * (l + 1)] - r).max() < 2e-12 * np.sqrt(2 * l + 1), l      # sums of 2l+1 terms of size ~1
+    # a rotation preserves the norm of every l block (unitarity of D^l)
+    for l in range(lmax + 1):
+        n_in = np.linalg.norm(np.broadcast_to(alm[..., l * l:(l + 1) ** 2], (nb, 2 * l + 1)), axis=1)
+        assert np.abs(np.linalg.norm(got[:, l * l:(l + 1) ** 2], axis=1) - n_in).max() < 1e-11 * (1 + n_in.max())
+
+
+def test_rotate_sh_lmax512_device_path(engine):
+    """cfg-4's consumer at its size: lmax = 512 on a 512-rotation slab, device buffers; sampled l against the oracle, norm
+    preservation and the composition rule R(-gamma, -beta, -alpha) R(alpha, beta, gamma) = 1 on everything"""
+    import torch
+    dev = "cuda:0"
+    lmax, nb = 512, 512
+    L2 = (lmax + 1) ** 2
+    gen = torch.Generator(device=dev).manual_seed(5)
+    alm = torch.complex(torch.randn(L2, dtype=torch.float64, device=dev, generator=gen), torch.randn(L2, dtype=torch.float64, device=dev, generator=gen))
+    a = torch.rand(nb, dtype=torch.float64, device=dev, generator=gen) * (2 * pi)
+    g = torch.rand(nb, dtype=torch.float64, device=dev, generator=gen) * (2 * pi)
+    b = torch.linspace(0.0, pi, nb, dtype=torch.float64, device=dev)
+    out = engine.rotate_sh(lmax, alm, a, b, g)
+    back = engine.rotate_sh(lmax, out, -g, -b, -a)                 # one coefficient set per rotation: the inverse rotation
+    torch.cuda.synchronize()
+    assert float((back - alm[None, :]).abs().max()) < 2e-10        # 1025 terms of size ~3, twice
+    lidx = torch.repeat_interleave(torch.arange(lmax + 1, device=dev), 2 * torch.arange(lmax + 1, device=dev) + 1)
+    n_in = torch.zeros(lmax + 1, dtype=torch.float64, device=dev).index_add_(0, lidx, alm.abs() ** 2)
+    n_out = torch.zeros((nb, lmax + 1), dtype=torch.float64, device=dev).index_add_(1, lidx, out.abs() ** 2)
+    assert float(((n_out - n_in[None, :]).abs() / (1 + n_in[None, :])).max()) < 1e-11
+    pick = np.array([0, 1, 17, 255, 256, 511])
+    ah, bh, gh, almh = a.cpu().numpy()[pick], b.cpu().numpy()[pick], g.cpu().numpy()[pick], alm.cpu().numpy()
+    ref = _rotate_ref(lmax, almh, ah, bh, gh, ls=[0, 1, 2, 100, 111, 112, 256, 511, 512])
+    oh = out[torch.from_numpy(pick).to(dev)].cpu().numpy()
+    for l, r in ref.items():
+        assert np.abs(oh[:, l * l:(l + 1) * (l + 1)] - r).max() < 1e-11 * np.sqrt(2 * l + 1), l
+    del out, back
+    torch.cuda.empty_cache()
+
+
+def test_rotate_sh_multi_handle_and_errors(engine):
+    import torch
+    rng = np.random.default_rng(7)
+    lmax, nb = 12, 37
+    L2 = (lmax + 1) ** 2
+    alm = rng.normal(size=(nb, L2)) + 1j * rng.normal(size=(nb, L2))
+    a, b, g = rng.uniform(0, 6, nb), rng.uniform(0, 3, nb), rng.uniform(0, 6, nb)
+    ref = engine.rotate_sh(lmax, alm, a, b, g)
+    eng = w.Engine(devices=[0, 1] if torch.cuda.device_count() >= 2 else [0, 0])
+    try:
+        assert np.abs(eng.rotate_sh(lmax, alm, a, b, g) - ref).max() < 1e-13
+        assert np.abs(eng.rotate_sh(lmax, alm[0], a, b, g) - engine.rotate_sh(lmax, alm[0], a, b, g)).max() < 1e-13
+    finally:
+        eng.close()
+    with pytest.raises(AssertionError):
+        engine.rotate_sh(lmax, alm[:, :-1], a, b, g)
+    with pytest.raises(AssertionError):
+        engine.rotate_sh(-1, alm, a, b, g)
+    assert engine.rotate_sh(3, np.zeros(16, complex), np.zeros(0), np.zeros(0), np.zeros(0)).shape == (0, 16)

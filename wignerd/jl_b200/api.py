@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "wd_launch_count", "wd_cache_clear", "wd_prepare", "wd_eigvecs", "wd_d_batch", "wd_D_batch",
     "wd_d_matrix", "wd_D_matrix", "wd_d_multi", "wd_djmn_batch", "wd_Djmn_batch", "wd_set_variant",
     "wd_fp64_peak", "wd_k2_shared_bytes", "wd_create_multi", "wd_multi_size", "wd_multi_child", "wd_shard_bounds",
-    "wd_gather", "wd_tables_save", "wd_tables_load", "wd_set_slab_bytes",
+    "wd_gather", "wd_tables_save", "wd_tables_load", "wd_set_slab_bytes", "wd_rotate_sh",
 ]
 
 
@@ -93,6 +93,7 @@ def load_library():
         L.wd_tables_save.argtypes = [vp, ctypes.c_char_p]
         L.wd_tables_load.argtypes = [vp, ctypes.c_char_p]
         L.wd_set_slab_bytes.argtypes = [vp, i64]
+        L.wd_rotate_sh.argtypes = [vp, i32, vp, i64, vp, vp, vp, i64, vp, ctypes.c_int]
         _lib = L
         return L
 
@@ -453,6 +454,46 @@ class Engine:
             v = out[int(offsets[k]):int(offsets[k]) + nb * N * N].reshape(nb, N, N)
             views.append(v.transpose(1, 2) if mem == MEM_DEVICE else v.transpose(0, 2, 1))
         return out, offsets, views
+
+    def rotate_sh(self, lmax: int, alm, alphas, betas, gammas, out=None):
+        """rotated spherical-harmonic coefficients ``res[b, l^2 + l + m'] = sum_m D^l_{m m'}(alpha_b, beta_b, gamma_b)
+        alm[(b,) l^2 + l + m]`` for l <= lmax (docs/src/index.md:76-84), without forming a D matrix.  ``alm``: complex128,
+        shape ((lmax+1)^2,) -- one set rotated by every rotation -- or (nb, (lmax+1)^2)."""
+        lmax = int(lmax)
+        L2 = (lmax + 1) ** 2
+        a, mem = self._angles(alphas)
+        b, mem_b = self._angles(betas)
+        g, mem_g = self._angles(gammas)
+        if not (mem == mem_b == mem_g):
+            raise AssertionError("alpha, beta, gamma must live in the same memory space")
+        nb = b.numel() if mem == MEM_DEVICE else b.size
+        if not ((a.numel() if mem == MEM_DEVICE else a.size) == nb == (g.numel() if mem == MEM_DEVICE else g.size)):
+            raise AssertionError("alpha, beta, gamma must have the same length")
+        if mem == MEM_DEVICE:
+            import torch
+            if not _is_torch(alm) or str(alm.dtype) != "torch.complex128" or not alm.is_contiguous():
+                raise AssertionError("alm must be a contiguous complex128 tensor when the angles are device tensors")
+            self._check_device(alm, "alm")
+            n_alm = alm.numel()
+        else:
+            alm = np.ascontiguousarray(alm, dtype=np.complex128)
+            n_alm = alm.size
+        if n_alm == L2:
+            stride = 0
+        elif n_alm == nb * L2:
+            stride = L2
+        else:
+            raise AssertionError(f"alm must hold (lmax+1)^2 = {L2} or nb x (lmax+1)^2 = {nb * L2} coefficients, got {n_alm}")
+        if mem == MEM_DEVICE:
+            if out is None:
+                out = torch.empty((nb, L2), dtype=torch.complex128, device=b.device)
+            self._use_torch_stream(b.device)
+        elif out is None:
+            out = np.empty((nb, L2), dtype=np.complex128)
+        out = self._check_out(out, mem, (nb, L2), True).reshape(nb, L2)
+        _check(self._lib.wd_rotate_sh(self._h, lmax, _ptr(alm), stride, _ptr(a), _ptr(b), _ptr(g), nb, _ptr(out), mem))
+        self._prepared.update(range(0, 2 * lmax + 1, 2))
+        return out
 
     # -- batched single elements ----------------------------------------------------------
     def _tuples(self, js, ms, ns):

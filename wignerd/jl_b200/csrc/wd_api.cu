@@ -8,6 +8,7 @@
 #include "wd_k2_dmma.cuh"
 #include "wd_k2_stream.cuh"
 #include "wd_k2_col.cuh"
+#include "wd_rotate.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -114,6 +115,7 @@ struct Plan {
     double *uq = nullptr, *mu = nullptr, *w = nullptr;
     double *uqc = nullptr;          // chunk-major copy of uq for the streaming kernel, built on first use
     int uqc_qpad = 0;
+    double *ufull = nullptr;        // full N x N eigenvector matrix (column-major, ld = N) for wd_rotate_sh, built on first use
 };
 
 }  // namespace
@@ -531,7 +533,8 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
         }
         // auto: symmetric grids (beta[b] + beta[nb-1-b] = pi) -> column kernel with pairing, everything else -> k2_real_kernel.
         // Both are launched; the device-side check lets exactly one of them work (an empty launch costs ~3 us).
-        if (cfits && fits && h->pairing && nb >= 4 * K2C_ANG) {
+        // (small batches are launch-latency bound -- 17 us at cfg-1 -- and stay with the one kernel)
+        if (cfits && fits && h->pairing && (double)nb * pl.dev.N * pl.dev.N >= 16.0e6) {
             const int *flag = nullptr;
             int rc = launch_col(h, a, csm, 0, &flag);
             if (rc) return rc;
@@ -677,6 +680,51 @@ int contract_host(wd_handle_t h, const Plan &pl, const double *alpha, const doub
     return WD_OK;
 }
 
+// Rotation of spherical-harmonic coefficients, all pointers on the device (wd_rotate.cuh): per l one phase kernel and two
+// tensor-core GEMMs with the full eigenvector matrix of l, on the handle's stream.
+int rotate_device(wd_handle_t h, int lmax, const double *alm, long long alm_stride, const double *alpha, const double *beta,
+                  const double *gamma, long long nb, double *out)
+{
+    if (nb <= 0) return WD_OK;
+    const long long L2 = (long long)(lmax + 1) * (lmax + 1);
+    const int Nmax = 2 * lmax + 1;
+    double *ws = nullptr;                                  // c and z: Nmax x nb complex each
+    const size_t wsn = (size_t)Nmax * nb * 2;
+    if (h->pool) CU(cudaMallocFromPoolAsync(&ws, 2 * wsn * sizeof(double), h->pool, h->stream));
+    else CU(cudaMallocAsync(&ws, 2 * wsn * sizeof(double), h->stream));
+    double *cbuf = ws, *zbuf = ws + wsn;
+    int rc = WD_OK;
+    for (int l = lmax; l >= 0 && rc == WD_OK; --l) {
+        Plan &pl = h->plans[2 * l];
+        const int N = 2 * l + 1;
+        if (!pl.ufull) {
+            double *u = nullptr;
+            if (cudaMalloc(&u, (size_t)N * N * sizeof(double)) != cudaSuccess) { rc = fail(WD_ERR_NOMEM, "cudaMalloc of the full eigenvector matrix of l = %d failed", l); break; }
+            k5_expand_u_kernel<<<(int)std::min<long long>(((long long)N * N + 255) / 256, (long long)h->num_sms * 8), 256, 0, h->stream>>>(pl.dev, u, N);
+            h->launches++;
+            cudaError_t e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);       // one-time per l: finish before the pointer is published
+            if (e != cudaSuccess) { cudaFree(u); rc = fail(WD_ERR_CUDA, "expanding the eigenvectors of l = %d failed: %s", l, cudaGetErrorString(e)); break; }
+            pl.ufull = u;
+        }
+        const long long work = (long long)N * nb;
+        k5_prephase_kernel<<<(int)std::min<long long>((work + 255) / 256, (long long)h->num_sms * 16), 256, 0, h->stream>>>(
+            reinterpret_cast<const double2 *>(alm), alm_stride, l, alpha, nb, reinterpret_cast<double2 *>(cbuf));
+        K5Args g;
+        g.U = pl.ufull; g.ld = N; g.N = N; g.l = l; g.nb = nb; g.out_stride = L2;
+        dim3 grid((unsigned)((2 * nb + K5_TN - 1) / K5_TN), (unsigned)((N + K5_TM - 1) / K5_TM));
+        g.in = cbuf; g.out = zbuf; g.angle = beta;
+        k5_gemm_kernel<true><<<grid, 256, 0, h->stream>>>(g);
+        g.in = zbuf; g.out = out; g.angle = gamma;
+        k5_gemm_kernel<false><<<grid, 256, 0, h->stream>>>(g);
+        h->launches += 3;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(WD_ERR_CUDA, "rotation kernels of l = %d failed to launch: %s", l, cudaGetErrorString(e));
+    }
+    cudaFreeAsync(ws, h->stream);
+    return rc;
+}
+
 __global__ void pole_kernel(double *D, int twoj, int kind, int cplx, double alpha, double gamma)
 {
     // wignerd!(…, NorthPole/SouthPole) (src/WignerD.jl:247-264) then, for complex D, the phase loop :338-340
@@ -806,12 +854,20 @@ int jmn_common(wd_handle_t h, const int32_t *twoj, const int32_t *twom, const in
         if (beta_kind == WD_BETA_GENERIC || beta_kind == WD_BETA_EQUATOR) {
             // only the j values that occur are decomposed and cached, like the reference's Jy_eigen (:163-176)
             cudaMemsetAsync(h->d_flag, 0, 2 * sizeof(int), h->stream);
-            cudaMemsetAsync(h->d_present, 0, (kMaxTwoJ + 2) * sizeof(int), h->stream);
-            mark_twoj_kernel<<<(int)std::min<long long>(1024, (n + 255) / 256), 256, 0, h->stream>>>(d_tj, n, h->d_present, kMaxTwoJ);
-            h->launches++;
-            std::vector<int> present((size_t)kMaxTwoJ + 2);
-            if (cudaMemcpyAsync(present.data(), h->d_present, present.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
-                cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = fail(WD_ERR_CUDA, "scan of the j values failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+            std::vector<int> present((size_t)kMaxTwoJ + 2, 0);
+            if (mem == WD_MEM_HOST) {
+                // host tuples: scan them here (a scalar call then needs one synchronisation, not two)
+                for (int64_t i = 0; i < n; ++i) {
+                    const int t = twoj[i];
+                    if (t < 0) present[kMaxTwoJ + 1] |= 1; else if (t > kMaxTwoJ) present[kMaxTwoJ + 1] |= 2; else present[t] = 1;
+                }
+            } else {
+                cudaMemsetAsync(h->d_present, 0, (kMaxTwoJ + 2) * sizeof(int), h->stream);
+                mark_twoj_kernel<<<(int)std::min<long long>(1024, (n + 255) / 256), 256, 0, h->stream>>>(d_tj, n, h->d_present, kMaxTwoJ);
+                h->launches++;
+                if (cudaMemcpyAsync(present.data(), h->d_present, present.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+                    cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = fail(WD_ERR_CUDA, "scan of the j values failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+            }
             if (present[kMaxTwoJ + 1] & 1) { rc = fail(WD_ERR_ASSERT, "j must be >= 0"); break; }
             if (present[kMaxTwoJ + 1] & 2) { rc = fail(WD_ERR_UNSUPPORTED, "2j exceeds the supported maximum %d", kMaxTwoJ); break; }
             std::vector<int32_t> all;
@@ -877,7 +933,7 @@ static void destroy_single(wd_handle_t h)
 {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (auto &kv : h->plans) { cudaFree(kv.second.uq); if (kv.second.uqc) cudaFree(kv.second.uqc); }
+    for (auto &kv : h->plans) { cudaFree(kv.second.uq); if (kv.second.uqc) cudaFree(kv.second.uqc); if (kv.second.ufull) cudaFree(kv.second.ufull); }
     if (h->d_table) cudaFree(h->d_table);
     if (h->d_flag) cudaFree(h->d_flag);
     if (h->d_pair) cudaFree(h->d_pair);
@@ -1042,7 +1098,7 @@ int wd_cache_clear(wd_handle_t h)
     std::lock_guard<std::mutex> lk(h->mtx);
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (auto &kv : h->plans) { cudaFree(kv.second.uq); if (kv.second.uqc) cudaFree(kv.second.uqc); }
+    for (auto &kv : h->plans) { cudaFree(kv.second.uq); if (kv.second.uqc) cudaFree(kv.second.uqc); if (kv.second.ufull) cudaFree(kv.second.ufull); }
     h->plans.clear();
     h->table_dirty = true;
     if (h->pool) cudaMemPoolTrimTo(h->pool, 0);
@@ -1234,6 +1290,86 @@ int wd_Djmn_batch(wd_handle_t h, const int32_t *twoj, const int32_t *twom, const
                   const double *beta, const double *gamma, int64_t n, int beta_kind, double *out, int mem)
 {
     return jmn_common(h, twoj, twom, twon, alpha, beta, gamma, n, beta_kind, out, mem, true);
+}
+
+int wd_rotate_sh(wd_handle_t h, int32_t lmax, const double *alm, int64_t alm_stride, const double *alpha, const double *beta,
+                 const double *gamma, int64_t nb, double *out, int mem)
+{
+    if (!h) return fail(WD_ERR_ASSERT, "null handle");
+    if (lmax < 0) return fail(WD_ERR_ASSERT, "lmax must be >= 0");
+    if (2 * (int64_t)lmax > kMaxTwoJ) return fail(WD_ERR_UNSUPPORTED, "lmax = %d exceeds the supported maximum %d", lmax, kMaxTwoJ / 2);
+    if (nb < 0) return fail(WD_ERR_ASSERT, "negative batch size");
+    if (nb == 0) return WD_OK;
+    if (!alm || !alpha || !beta || !gamma || !out) return fail(WD_ERR_ASSERT, "null pointer argument");
+    if (mem != WD_MEM_HOST && mem != WD_MEM_DEVICE) return fail(WD_ERR_ASSERT, "bad mem flag %d", mem);
+    const int64_t L2 = (int64_t)(lmax + 1) * (lmax + 1);
+    if (alm_stride != 0 && alm_stride < L2) return fail(WD_ERR_ASSERT, "alm_stride must be 0 (one shared set) or >= (lmax+1)^2 = %lld", (long long)L2);
+    if (!h->children.empty()) {
+        if (mem != WD_MEM_HOST) return fail(WD_ERR_UNSUPPORTED, "a multi-GPU handle takes host buffers; for device buffers use the per-device handles (wd_multi_child)");
+        const int R = (int)h->children.size();
+        return for_each_child(h, [=](wd_handle_t c, int r) {
+            long long lo, hi;
+            shard_bounds(nb, r, R, 1, &lo, &hi);
+            if (hi <= lo) return (int)WD_OK;
+            return wd_rotate_sh(c, lmax, alm + 2 * (size_t)lo * alm_stride, alm_stride, alpha + lo, beta + lo, gamma + lo, hi - lo,
+                                out + 2 * (size_t)lo * L2, mem);
+        });
+    }
+    std::lock_guard<std::mutex> lk(h->mtx);
+    std::vector<int32_t> js((size_t)lmax + 1);
+    for (int l = 0; l <= lmax; ++l) js[l] = 2 * l;
+    int rc = prepare_locked(h, js.data(), (int)js.size());
+    if (rc) return rc;
+    CU(cudaSetDevice(h->device));
+    if (mem == WD_MEM_DEVICE) return rotate_device(h, lmax, alm, alm_stride, alpha, beta, gamma, nb, out);
+    // host buffers: coefficients and angles in, rotated coefficients out, in slabs of rotations (two output slabs in flight)
+    const size_t per = 2 * (size_t)L2;                                            // doubles per rotation
+    const size_t alm_doubles = alm_stride ? 2 * (size_t)alm_stride * nb : per;
+    double *d_in = nullptr;
+    CU(cudaMalloc(&d_in, (alm_doubles + 3 * (size_t)nb) * sizeof(double)));
+    double *d_ang = d_in + alm_doubles;
+    cudaMemcpyAsync(d_in, alm, alm_doubles * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(d_ang, alpha, nb * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(d_ang + nb, beta, nb * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(d_ang + 2 * nb, gamma, nb * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    const bool pinned = (size_t)nb * per * sizeof(double) < ((size_t)8 << 20) || host_is_pinned(out);
+    // at least 1024 rotations per slab: the GEMMs need >= ~300 column tiles to fill the GPU (4.3 GB per slab at lmax = 512)
+    long long slab = std::min<long long>(nb, std::max<long long>(1024, (long long)(h->slab_bytes / (per * sizeof(double)))));
+    const int nbuf = slab < nb ? 2 : 1;
+    auto grow = [](double **buf, size_t *have, size_t need) -> cudaError_t {
+        if (*have >= need) return cudaSuccess;
+        if (*buf) cudaFree(*buf);
+        *buf = nullptr; *have = 0;
+        cudaError_t e = cudaMalloc(buf, need);
+        if (e == cudaSuccess) *have = need;
+        return e;
+    };
+    for (int i = 0; i < nbuf && rc == WD_OK; ++i) {
+        if (grow(&h->ws_slab[i], &h->ws_slab_bytes[i], (size_t)slab * per * sizeof(double)) != cudaSuccess)
+            rc = fail(WD_ERR_NOMEM, "cudaMalloc of a %zu-byte output slab failed", (size_t)slab * per * sizeof(double));
+        if (!h->ev_done[i]) {
+            cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming);
+        }
+    }
+    int k = 0;
+    for (long long b0 = 0; b0 < nb && rc == WD_OK; b0 += slab, ++k) {
+        const int i = k % nbuf;
+        const long long cnt = std::min(slab, nb - b0);
+        if (k >= nbuf) cudaStreamWaitEvent(h->stream, h->ev_copied[i], 0);
+        rc = rotate_device(h, lmax, d_in + (alm_stride ? 2 * (size_t)alm_stride * b0 : 0), alm_stride, d_ang + b0, d_ang + nb + b0,
+                           d_ang + 2 * nb + b0, cnt, h->ws_slab[i]);
+        if (rc) break;
+        cudaEventRecord(h->ev_done[i], h->stream);
+        cudaStreamWaitEvent(h->copy_stream, h->ev_done[i], 0);
+        rc = copy_out(h, (char *)(out + (size_t)b0 * per), (const char *)h->ws_slab[i], (size_t)cnt * per * sizeof(double), pinned);
+        cudaEventRecord(h->ev_copied[i], h->copy_stream);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(h->stream), e2 = cudaStreamSynchronize(h->copy_stream);
+    cudaFree(d_in);
+    if (rc) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess) return fail(WD_ERR_CUDA, "rotation failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    return WD_OK;
 }
 
 int wd_set_slab_bytes(wd_handle_t h, int64_t bytes)
