@@ -508,6 +508,54 @@ def bench_multi(ctx, name, cfg, steps, warmup, e2e=True):
     return rec
 
 
+def bench_rotate(ctx, steps, warmup):
+    """the consumer of cfg-4: rotate one set of spherical-harmonic coefficients to lmax = 512 by the rank's
+    4096 / N rotations -- wd_rotate_sh works from the eigenvectors (two tensor-core GEMMs per l), no d matrix is formed"""
+    torch, eng = ctx.torch, ctx.eng
+    lmax = 512
+    nb = max(16, 4096 // ctx.world)
+    L2 = (lmax + 1) ** 2
+    gen = torch.Generator(device=ctx.dev).manual_seed(4 + ctx.rank)
+    alm = torch.complex(torch.randn(L2, dtype=torch.float64, device=ctx.dev, generator=gen), torch.randn(L2, dtype=torch.float64, device=ctx.dev, generator=gen))
+    beta = symmetric_betas(ctx, nb)
+    alpha = torch.rand(nb, dtype=torch.float64, device=ctx.dev, generator=gen) * (2 * np.pi)
+    gamma = torch.rand(nb, dtype=torch.float64, device=ctx.dev, generator=gen) * (2 * np.pi)
+    out = torch.empty((nb, L2), dtype=torch.complex128, device=ctx.dev)
+    step = lambda: eng.rotate_sh(lmax, alm, alpha, beta, gamma, out=out)      # noqa: E731
+    for _ in range(warmup):
+        step()
+    ctx.barrier()
+    l0 = eng.launch_count()
+    ms_max, ms_rank = gpu_time(ctx, step, steps, 0)
+    launches = eng.launch_count() - l0
+    flops = 8.0 * nb * sum((2 * l + 1) ** 2 for l in range(lmax + 1))        # two N x N real x (nb complex) products per l
+    d_elems = nb * sum((2 * l + 1) ** 2 for l in range(lmax + 1))            # the D-matrix elements this call stands for
+    t = ms_rank * 1e-3
+    rec = {"ms_per_step": ms_max, "value": nb * L2 * ctx.world / (ms_max * 1e-3), "unit": "rotated coefficients/s", "steps": steps,
+           "gpu_launches": int(launches), "rotations_per_gpu": nb, "lmax": lmax,
+           "equivalent_d_elements_per_s": d_elems * ctx.world / (ms_max * 1e-3),
+           "note": "the same rotations through the matrices would need every d^l(beta) of cfg4 (5.9 TB at 4096 angles); "
+                   "equivalent_d_elements_per_s counts the D elements that were never formed"}
+    p64 = ctx.fp64.get("peak_tflops")
+    if p64:
+        rec["roofline"] = {"bound": "tensor", "achieved": flops / t / 1e12, "peak": p64, "unit": "TFLOP/s", "frac": flops / t / 1e12 / p64,
+                           "traffic": None, "kernel": "k5_gemm_kernel", "algorithmic_flops_per_launch": flops, "peak_source": ctx.fp64["peak_source"]}
+    del out
+    torch.cuda.empty_cache()
+    ne = min(nb, 1024)
+    ho = pinned_empty(ctx, (ne, L2), torch.complex128)
+    if ho is not None:
+        ha, hb, hg = alpha[:ne].cpu().numpy(), beta[:ne].cpu().numpy(), gamma[:ne].cpu().numpy()
+        halm = alm.cpu().numpy()
+        dt_max, dt_rank = wall_time(ctx, lambda: eng.rotate_sh(lmax, halm, ha, hb, hg, out=ho.numpy()), 2, 1)
+        rec["e2e"] = {"value": ne * L2 * ctx.world / dt_max, "unit": "rotated coefficients/s", "h2d_bytes_per_step": L2 * 16 + ne * 24,
+                      "d2h_bytes_per_step": ne * L2 * 16, "steps": 2, "rotations_per_gpu": ne,
+                      "kernel_share_of_e2e": (ms_rank * 1e-3 * ne / nb) / dt_rank,
+                      "note": "wd_rotate_sh with HOST buffers (coefficients and angles in, rotated coefficients out)"}
+        del ho
+    return rec
+
+
 def bench_jmn(ctx, name, cfg, steps, warmup, e2e=True):
     torch, eng = ctx.torch, ctx.eng
     n = cfg["nb"]
@@ -752,6 +800,7 @@ def main():
         sub["cfg2_random_grid"] = bench_matrices(ctx, "cfg2", CONFIGS["cfg2"], sub_steps, 3, grid="random", e2e=False)
         sub["cfg3"] = bench_matrices(ctx, "cfg3", CONFIGS["cfg3"], sub_steps, 3)
         sub["cfg4"] = bench_multi(ctx, "cfg4", CONFIGS["cfg4"], 2 if ctx.world < 4 else 3, 1)
+        sub["cfg4_rotate_sh"] = bench_rotate(ctx, 3, 1)
         sub["cfg5"] = bench_jmn(ctx, "cfg5", CONFIGS["cfg5"], sub_steps, 3)
         line["strong"] = strong_scaling(ctx, max(5, min(args.steps, 20)))
         line["host_copy_ceiling"] = host_copy_ceiling(ctx)
@@ -759,7 +808,8 @@ def main():
             line["eigen_setup"] = eigen_setup(ctx)
             if not args.no_cpu_baseline:
                 for name, rec in sub.items():
-                    rec["cpu_baseline"] = cpu_baseline_for(name.split("_")[0], CONFIGS[name.split("_")[0]])
+                    if name != "cfg4_rotate_sh":
+                        rec["cpu_baseline"] = cpu_baseline_for(name.split("_")[0], CONFIGS[name.split("_")[0]])
         line["configs"] = sub
     if ctx.rank == 0 and not args.no_cpu_baseline:
         cb = cpu_baseline_for(args.config, cfg)

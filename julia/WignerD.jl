@@ -40,7 +40,23 @@ function Handle(device::Integer = parse(Int, get(ENV, "WIGNERD_B200_DEVICE", "0"
     finalizer(x -> ccall((:wd_destroy, libwd), Cint, (Ptr{Cvoid},), x.ptr), h)
     return h
 end
+# several GPUs behind one handle (wd_create_multi): the batched methods then shard their host arrays over the devices
+function Handle(devices::AbstractVector{<:Integer})
+    ref = Ref{Ptr{Cvoid}}(C_NULL)
+    devs = Vector{Cint}(devices)
+    check(ccall((:wd_create_multi, libwd), Cint, (Cint, Ptr{Cint}, Ref{Ptr{Cvoid}}), length(devs), devs, ref))
+    h = Handle(ref[])
+    finalizer(x -> ccall((:wd_destroy, libwd), Cint, (Ptr{Cvoid},), x.ptr), h)
+    return h
+end
 handle() = get!(() -> Handle(), task_local_storage(), :wignerd_b200_handle)::Handle
+# use_devices!([0, 1, ..., 7]): this Task's calls run on all listed GPUs from now on
+use_devices!(devices::AbstractVector{<:Integer}) = (task_local_storage(:wignerd_b200_handle, Handle(devices)); nothing)
+ndevices() = Int(ccall((:wd_multi_size, libwd), Cint, (Ptr{Cvoid},), handle().ptr))
+
+# persisted eigenvector tables: a cold process loads them instead of running the eigensolver (extends Jy_eigen's cache)
+save_tables(path::AbstractString) = check(ccall((:wd_tables_save, libwd), Cint, (Ptr{Cvoid}, Cstring), handle().ptr, path))
+load_tables(path::AbstractString) = check(ccall((:wd_tables_load, libwd), Cint, (Ptr{Cvoid}, Cstring), handle().ptr, path))
 
 # ---- special co-latitudes: Real subtypes accepted wherever beta is ----------------------------------------
 abstract type SpecialCoLatitudes <: Real end
@@ -174,6 +190,26 @@ function wignerdjmn(j::AbstractVector, m::AbstractVector, n::AbstractVector, bet
     check(ccall((:wd_djmn_batch, libwd), Cint,
                 (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Int64, Cint, Ptr{Float64}, Cint),
                 handle().ptr, tj, tm, tn, b, length(b), Cint(0), out, WD_MEM_HOST))
+    return out
+end
+
+
+# rotated spherical-harmonic coefficients, out[l^2 + l + m' + 1, b] = sum_m D^l_{m m'}(alpha_b, beta_b, gamma_b) alm[l^2 + l + m + 1 (, b)]
+# for l = 0..lmax (docs/src/index.md:76-84 of the reference), without forming a D matrix.  alm: a vector of (lmax+1)^2 coefficients
+# rotated by every rotation, or a (lmax+1)^2 x nb matrix (one set per rotation).
+function rotate_sh(lmax::Integer, alm::AbstractVecOrMat{<:Number}, alpha::AbstractVector{<:Real}, beta::AbstractVector{<:Real},
+                   gamma::AbstractVector{<:Real})
+    L2 = (Int(lmax) + 1)^2
+    a, b, g = Vector{Float64}(alpha), Vector{Float64}(beta), Vector{Float64}(gamma)
+    @assert length(a) == length(b) == length(g)
+    A = Array{ComplexF64}(alm)
+    @assert size(A, 1) == L2 "alm must hold (lmax+1)^2 coefficients per set"
+    stride = ndims(A) == 1 ? 0 : L2
+    ndims(A) == 2 && @assert size(A, 2) == length(b)
+    out = Array{ComplexF64}(undef, L2, length(b))
+    check(ccall((:wd_rotate_sh, libwd), Cint,
+                (Ptr{Cvoid}, Int32, Ptr{ComplexF64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{ComplexF64}, Cint),
+                handle().ptr, Int32(lmax), A, stride, a, b, g, length(b), out, WD_MEM_HOST))
     return out
 end
 

@@ -180,3 +180,16 @@ def test_column_kernel_range_and_new_entry_points_reject_nulls():
     assert L.wd_tables_save(None, b"/tmp/x") == 2 and L.wd_tables_load(None, None) == 2
     assert L.wd_gather(None, None, None, 0, None) == 2
     assert L.wd_set_slab_bytes(None, 1 << 20) == 2
+
+
+def test_c_program_links_against_every_entry_point(tmp_path):
+    """a C (not C++, not Python) consumer: the header compiles as C and every declared symbol links and is callable"""
+    import subprocess
+    exe = str(tmp_path / "c_abi_link")
+    libdir = os.path.dirname(w.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_abi_link.c"), "-o", exe, "-L", libdir, "-lwignerd_b200",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "c abi ok: 29 entry points" in out.stdout

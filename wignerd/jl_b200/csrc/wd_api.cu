@@ -342,6 +342,10 @@ int launch_real(wd_handle_t h, const K2Args &a, size_t smem)
 
 // Column-staged DMMA kernel for real d (k2_col_kernel, wd_k2_col.cuh): the default for tables that fit in shared memory
 constexpr int kPairRing = 64;
+// beta <-> pi - beta pairing: the mirror matrix is computed from the trig values of its partner, so a grid counts as symmetric
+// when |beta[b] + beta[nb-1-b] - pi| <= tol for every b; |d d/d beta| <= j bounds the extra error of the mirror matrix by
+// j * tol <= 5e-13 (2e-13 up to j = 100; a linspace grid deviates by <= 8e-16).
+double pair_tol(int twoj) { return std::min(2e-15, 5e-13 / (double)std::max(1, twoj / 2)); }
 bool col_fits(wd_handle_t h, const PlanDev &p, size_t *bytes)
 {
     const K2CSmem L = k2c_smem_layout(p.Q, p.Kp, p.ldu, p.N);
@@ -382,12 +386,10 @@ int launch_col(wd_handle_t h, const K2Args &a, size_t smem, int mode, const int 
         if (e) c.handoff = atoi(e);
 #endif
     }
-    // beta <-> pi - beta pairing: decided on the device, no host round trip.  The mirror matrix is computed
-    // from the trig values of its partner: |beta[b] + beta[nb-1-b] - pi| <= tol bounds the extra error by j * tol = 2e-13.
+    // beta <-> pi - beta pairing: decided on the device, no host round trip (pair_tol)
     if (mode != 2) {
         int *flag = h->d_pair + (h->pair_idx++ % kPairRing);
-        const double tol = 2e-13 / (double)std::max(1, a.p.twoj / 2);
-        k2c_pair_check_kernel<<<1, 1024, 0, h->stream>>>(a.beta, a.nb, tol, flag);
+        k2c_pair_check_kernel<<<1, 1024, 0, h->stream>>>(a.beta, a.nb, pair_tol(a.p.twoj), flag);
         h->launches++;
         c.pair_flag = flag;
         if (flag_out) *flag_out = flag;
@@ -466,6 +468,14 @@ int launch_stream(wd_handle_t h, const Plan &cpl, const K2Args &a)
         sa.base.out = a.out + (size_t)b0 * a.p.N * a.p.N;
         sa.nck0 = nck0; sa.nck1 = nck1;
         sa.uqc = pl.uqc; sa.qpad = pl.uqc_qpad;
+        // symmetric grids: pairing, decided on the device (only when the batch is not cut into slabs)
+        sa.pair_flag = nullptr;
+        if (h->pairing && nac_all <= nac_cap && a.nb >= 32) {
+            int *flag = h->d_pair + (h->pair_idx++ % kPairRing);
+            k2c_pair_check_kernel<<<1, 1024, 0, h->stream>>>(a.beta, a.nb, pair_tol(a.p.twoj), flag);
+            h->launches++;
+            sa.pair_flag = flag;
+        }
         const size_t ntrig = (size_t)nac * nck * K2S_TRIG_TILE;
         double *trig = nullptr;
         if (h->pool) CU(cudaMallocFromPoolAsync(&trig, ntrig * sizeof(double), h->pool, h->stream));
@@ -473,7 +483,7 @@ int launch_stream(wd_handle_t h, const Plan &cpl, const K2Args &a)
         sa.trig = trig;
         const long long work = nac * nck * K2_ANG * K2S_KC;
         const int tblocks = (int)std::min<long long>((work + 255) / 256, (long long)h->num_sms * 16);
-        k2s_trig_kernel<<<tblocks, 256, 0, h->stream>>>(a.p, sa.base.beta, cnt, trig, sa.nck0, sa.nck1);
+        k2s_trig_kernel<<<tblocks, 256, 0, h->stream>>>(a.p, sa.base.beta, cnt, trig, sa.nck0, sa.nck1, sa.pair_flag);
         const int gmax = HALF ? 2 : 4;
         const int ngroups = (a.p.Q + 15) / 16;
         const long long ntiles = nac * ((ngroups + gmax - 1) / gmax) * ((a.p.Q + K2_CWARPS - 1) / K2_CWARPS);
@@ -884,9 +894,9 @@ int jmn_common(wd_handle_t h, const int32_t *twoj, const int32_t *twom, const in
         a.twoj = d_tj; a.twom = d_tm; a.twon = d_tn;
         a.beta = d_b; a.alpha = d_a; a.gamma = d_g;
         a.n = n; a.beta_kind = beta_kind; a.out = d_out; a.err = h->d_flag;
-        const int blocks = (int)std::min<long long>((n + 7) / 8, (long long)h->num_sms * 8);
-        if (cplx) k4_jmn_kernel<true><<<blocks, 256, 0, h->stream>>>(a);
-        else k4_jmn_kernel<false><<<blocks, 256, 0, h->stream>>>(a);
+        const int blocks = (int)std::min<long long>((n + 32 * K4_WARPS - 1) / (32 * K4_WARPS), (long long)h->num_sms * 12);
+        if (cplx) k4_jmn_kernel<true><<<blocks, K4_WARPS * 32, 0, h->stream>>>(a);
+        else k4_jmn_kernel<false><<<blocks, K4_WARPS * 32, 0, h->stream>>>(a);
         h->launches++;
         if (mem == WD_MEM_HOST) cudaMemcpyAsync(stage ? (void *)(stage + stage_out_off) : (void *)out, d_out, osz, cudaMemcpyDeviceToHost, h->stream);
         cudaMemcpyAsync(hflag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream);

@@ -130,13 +130,65 @@ struct K2CWarp {                // per-warp state of the store path
     unsigned steps;             // staging steps so far (slot = steps & 1)
     unsigned have;              // bit t: target t has a held-back sector (a stretch of this block has been staged)
     int nostore;
+    int elem;                   // doubles per matrix element (1: real d).  A complex variant of this kernel (elem = 2, phase tables,
+                                // 16-byte staging stores) was built and dropped: 5.0 ms at cfg-3 against 4.0 ms of k2_cplx_kernel -- every
+                                // lane owns 4 consecutive rows, so its 16-byte stores hit 2 of 8 banks, and the phase multiplies
+                                // (6 FP64 operations per element and target) share the pipe with the DMMAs of the partner warp
 };
 
-// global element index (in doubles from address 0) of row 0 of column col of the matrix of angle x of the item
+// global index (in doubles from address 0) of row 0 of column col of the matrix of angle x of the item
 __device__ __forceinline__ unsigned long long k2c_e0(const K2CWarp &ws, const bool back, const int col, const int x)
 {
     const long long b = back ? ws.nb - 1 - (ws.f0 + x) : ws.f0 + x;
-    return ws.ebase + (unsigned long long)b * ws.NN + (unsigned long long)(col * ws.N);
+    return ws.ebase + (unsigned long long)ws.elem * ((unsigned long long)b * ws.NN + (unsigned long long)(col * ws.N));
+}
+
+// Second half of a staging step, after the values of the stretch (rows row0 .. row0 + nrows - 1 of column col) have been
+// written to the slot: splice the held-back sector of the previous stretch of the target's chain in, hold this stretch's
+// last partial sector back, and send the whole sectors off with one bulk-TMA store per angle.
+__device__ __forceinline__ void k2c_splice_issue(K2CWarp &ws, double *slot, const bool back, const int col, const int row0,
+                                                 const int nrows, const int t, const bool chain_asc, const bool have)
+{
+    const int lane = ws.lane, len = ws.elem * nrows, off0 = ws.elem * row0;
+    __syncwarp();
+    const int nv = back ? ws.nvB : ws.na;                             // angles of the item that exist for this target
+    if (lane < 3 * K2C_ANG) {                                         // lane -> (angle lane / 3, element lane % 3)
+        const int x = lane / 3, e = lane - 3 * x;
+        if (x < nv) {
+            const unsigned long long es = k2c_e0(ws, back, col, x) + off0;
+            const int ph = (int)(es & 3ull), pe = ph + len;
+            double *row = slot + x * ws.rs;
+            double *cy = ws.carry + (t * K2C_ANG + x) * 4 + e;
+            double *g0 = ws.out + (es - ws.ebase);                    // first double of the stretch in global memory
+            if (chain_asc) {
+                // carry-in: the ph doubles in front of the stretch; carry-out: its last pe & 3 doubles
+                if (e < ph) { if (have) row[e] = *cy; }
+                if (!have && ph > 0 && ph + e < 4 && !ws.nostore) g0[e] = row[ph + e];          // first stretch of the block: partial head sector
+                if (e < (pe & 3)) *cy = row[(pe & ~3) + e];
+            } else {
+                const int nin = (4 - (pe & 3)) & 3;
+                if (e < nin) { if (have) row[pe + e] = *cy; }
+                if (!have && e < (pe & 3) && !ws.nostore) g0[len - (pe & 3) + e] = row[(pe & ~3) + e];   // first stretch: partial tail sector
+                if (ph > 0 && ph + e < 4) *cy = row[ph + e];
+            }
+        }
+    }
+    fence_async_smem();
+    __syncwarp();
+    // lane -> angle.  (The compiler serialises the 8 copies -- UBLKCP takes uniform registers: ~11 instructions per copy;
+    // tried and dropped: one lane issuing all copies with shuffled parameters 7.4 ms, plain 16-byte vector stores of the
+    // staged windows instead of the TMA 17.9 ms, against 6.5 ms at cfg-2.)
+    if (lane < nv && !ws.nostore) {
+        const unsigned long long es = k2c_e0(ws, back, col, lane) + off0;
+        const int ph = (int)(es & 3ull), pe = ph + len;
+        int s0, s1;
+        if (chain_asc) { s0 = (ph > 0 && !have) ? 4 : 0; s1 = pe & ~3; }
+        else           { s0 = ph > 0 ? 4 : 0;            s1 = have ? (pe + 3) & ~3 : pe & ~3; }
+        if (s1 > s0) bulk_store(ws.out + ((es - ph) - ws.ebase) + s0, slot + lane * ws.rs + s0, (unsigned)(s1 - s0) * 8u);
+    }
+    bulk_commit();
+    ws.steps++;
+    ws.have |= 1u << t;
 }
 // One staging step = one STRETCH (half a column: its ascending part, rows i0 .. N-1 <- quadrant rows q = 0 .. Q-1, or its
 // descending part, rows i0-1 .. 0 <- q = zskip .. Q-1) of one target column, for the 8 angles of the item.  Every lane
@@ -154,7 +206,7 @@ template <bool DESCROWS, int GC>
 __device__ __forceinline__ void k2c_stage(K2CWarp &ws, const K2CVal (&v)[GC][4], const bool back,
                                           const int col, const int colsig, const int t, const bool chain_asc)
 {
-    const int Q = ws.Q, i0 = ws.i0, lane = ws.lane;
+    const int Q = ws.Q, i0 = ws.i0;
     const int row0 = DESCROWS ? 0 : i0, len = DESCROWS ? i0 : Q;
     // sign masks of the lane's rows jj = 0..3 of a group (16 g + 4 c vanish mod 4): sigma(row - colsig) [* (-1)^row for the
     // mirror matrix].  (Flipping the values in place, relative to their previous sign, saves a move per element but costs
@@ -183,45 +235,7 @@ __device__ __forceinline__ void k2c_stage(K2CWarp &ws, const K2CVal (&v)[GC][4],
             }
         }
     }
-    __syncwarp();
-    const int nv = back ? ws.nvB : ws.na;                             // angles of the item that exist for this target
-    if (lane < 3 * K2C_ANG) {                                         // lane -> (angle lane / 3, element lane % 3)
-        const int x = lane / 3, e = lane - 3 * x;
-        if (x < nv) {
-            const unsigned long long es = k2c_e0(ws, back, col, x) + row0;
-            const int ph = (int)(es & 3ull), pe = ph + len;
-            double *row = slot + x * ws.rs;
-            double *cy = ws.carry + (t * K2C_ANG + x) * 4 + e;
-            double *g0 = ws.out + (es - ws.ebase);                    // first element of the stretch in global memory
-            if (chain_asc) {
-                // carry-in: the ph elements in front of the stretch; carry-out: its last pe & 3 elements
-                if (e < ph) { if (have) row[e] = *cy; }
-                if (!have && ph > 0 && ph + e < 4 && !ws.nostore) g0[e] = row[ph + e];          // first stretch of the block: partial head sector
-                if (e < (pe & 3)) *cy = row[(pe & ~3) + e];
-            } else {
-                const int nin = (4 - (pe & 3)) & 3;
-                if (e < nin) { if (have) row[pe + e] = *cy; }
-                if (!have && e < (pe & 3) && !ws.nostore) g0[len - (pe & 3) + e] = row[(pe & ~3) + e];   // first stretch: partial tail sector
-                if (ph > 0 && ph + e < 4) *cy = row[ph + e];
-            }
-        }
-    }
-    fence_async_smem();
-    __syncwarp();
-    // lane -> angle.  (The compiler serialises the 8 copies -- UBLKCP takes uniform registers: ~11 instructions per copy;
-    // tried and dropped: one lane issuing all copies with shuffled parameters 7.4 ms, plain 16-byte vector stores of the
-    // staged windows instead of the TMA 17.9 ms, against 6.5 ms at cfg-2.)
-    if (lane < nv && !ws.nostore) {
-        const unsigned long long es = k2c_e0(ws, back, col, lane) + row0;
-        const int ph = (int)(es & 3ull), pe = ph + len;
-        int s0, s1;
-        if (chain_asc) { s0 = (ph > 0 && !have) ? 4 : 0; s1 = pe & ~3; }
-        else           { s0 = ph > 0 ? 4 : 0;            s1 = have ? (pe + 3) & ~3 : pe & ~3; }
-        if (s1 > s0) bulk_store(ws.out + ((es - ph) - ws.ebase) + s0, slot + lane * ws.rs + s0, (unsigned)(s1 - s0) * 8u);
-    }
-    bulk_commit();
-    ws.steps++;
-    ws.have |= 1u << t;
+    k2c_splice_issue(ws, slot, back, col, row0, len, t, chain_asc, have);
 }
 
 // end of a warp's column block: the held-back sectors leave through partial stores.  q_last: last quadrant column of the block.
@@ -233,7 +247,7 @@ __device__ __forceinline__ void k2c_flush(K2CWarp &ws, const int q_last)
     if (((ws.have >> t) & 1u) && x < (back ? ws.nvB : ws.na) && !ws.nostore) {
         const int col = asc ? ws.i0 + q_last : ws.Q - 1 - q_last;
         // last stretch of the chain: ascending chains end with the ascending part of the column, descending ones with the descending part
-        const int row0 = asc ? ws.i0 : 0, len = asc ? ws.Q : ws.i0;
+        const int row0 = ws.elem * (asc ? ws.i0 : 0), len = ws.elem * (asc ? ws.Q : ws.i0);
         const unsigned long long es = k2c_e0(ws, back, col, x) + row0;
         const int ph = (int)(es & 3ull), pe = ph + len;
         double *g0 = ws.out + (es - ws.ebase);
@@ -422,6 +436,7 @@ __global__ void __launch_bounds__(K2C_THREADS, 1) k2_col_kernel(K2CArgs a)
     ws.nvl = max(0, min(4, Q - 16 * (((Q + 15) >> 4) - 1) - 4 * (lane & 3)));
     ws.steps = 0; ws.have = 0;
     ws.nostore = (a.flags & K2C_FLAG_NOSTORE) != 0;
+    ws.elem = 1;
 
     // trig tables of item k+1 are made during item k (k2_real_kernel's scheme): Tc/Ts[angle][kp] = w cos|sin(mu beta),
     // fl(mu*beta) then sincos like src/WignerD.jl:199

@@ -441,6 +441,7 @@ __global__ void __launch_bounds__(K2_THREADS_CPLX, 1) k2_cplx_kernel(K2Args a)
 //   * the last, partial wave of chunks is split over several CTAs each (K2Args::tsplit).
 // ------------------------------------------------------------------------------------------------
 constexpr int K2_TILE_ASC = 1, K2_TILE_DESC = 2, K2_TILE_END_ALL = 8;
+constexpr int K2_TILE_MIRROR = 16;   // beta <-> pi - beta pairing: the tile also feeds the mirror matrices nb-1-b (ea2 / ed2)
 
 struct K2Tile {                 // descriptor of one staged half tile: 8 angles (one MMA row tile) x <= 64 quadrant rows
     unsigned long long ea;      // ascending target : element index of (first angle, position 0); position s lives at ea + s
@@ -449,9 +450,15 @@ struct K2Tile {                 // descriptor of one staged half tile: 8 angles 
     int s_lo_d;                 // descending target only: s >= s_lo_d (quadrant row >= zskip)
     int nrows;                  // existing angles of the tile (1..8); angle ar of the tile is matrix 2*ar further on
     int dib_a, dib_d;           // (row - col) mod 4 of position 0 in the two targets: sigma(dib_a + s), sigma(dib_d - s)
-    int kind;                   // K2_TILE_ASC | K2_TILE_DESC, or an END marker
+    int kind;                   // K2_TILE_ASC | K2_TILE_DESC [| K2_TILE_MIRROR], or an END marker
+    // pairing (d(pi-b)[m,n] = (-1)^(j+m) d(b)[m,-n], test/runtests.jl:330-334): the same staged values, with the row-alternating
+    // extra sign, go to the mirror matrix of every angle -- ascending into the column that is the descending target's in the
+    // front matrix and vice versa; angle ar of the tile is matrix 2*ar FURTHER BACK from ea2 / ed2
+    unsigned long long ea2, ed2;
+    int nrows2;                 // angles of the tile that have a mirror matrix (a prefix of nrows)
+    int par;                    // bit 0: parity of the row of position 0 in the ascending target, bit 1: in the descending one
 };
-static_assert(sizeof(K2Tile) == 40, "K2Tile layout");
+static_assert(sizeof(K2Tile) == 64, "K2Tile layout");
 
 struct K2RSmem {                // offsets in doubles, computed identically on host and device
     int uq, mu, w, trig, stg, desc, bars, total;
@@ -500,6 +507,8 @@ struct K2RCtx {                 // what a compute warp needs for its hand-offs
     unsigned tiles;             // tiles handed over so far
     size_t NN, e_item, e_ip, e_ipr;     // N*N; element index of the item's first matrix; of output columns i', i'r in it
     int ntiles, nrows0, nrows1; // existing angle tiles of the item and their angle counts (ragged last chunk)
+    int paired, nrowsb0, nrowsb1;       // pairing: angles of the two tiles that have a mirror matrix
+    size_t e_item_b;            // element index of the mirror matrix of the item's first angle
 };
 
 // Stage one butterfly result (S or D) of a unit, one angle tile at a time, and hand it to the store warp.
@@ -529,6 +538,17 @@ __device__ __forceinline__ void k2_emit(const K2Args &a, const K2Ctx &cx, K2RCtx
             const int col_a = isD ? cx.N - 1 - ip : ip, col_d = isD ? ip : cx.N - 1 - ip;
             d.dib_a = (row_a - col_a) & 3; d.dib_d = (row_d - col_d) & 3;
             d.kind = a.nostore ? 0 : (isD ? (K2_TILE_DESC | (both ? K2_TILE_ASC : 0)) : (K2_TILE_ASC | (both ? K2_TILE_DESC : 0)));
+            d.ea2 = d.ed2 = 0; d.nrows2 = 0; d.par = 0;
+            if (rc.paired && d.kind) {
+                // mirror matrix: S -> (i, i'r) upwards, (ir, i') downwards;  D -> (i, i') upwards, (ir, i'r) downwards
+                const size_t eb = rc.e_item_b - (ai ? rc.NN : 0);
+                const size_t c_ip = (size_t)ip * cx.N, c_ipr = (size_t)(cx.N - 1 - ip) * cx.N;
+                d.ea2 = eb + (isD ? c_ip : c_ipr) + row_a;
+                d.ed2 = eb + (isD ? c_ipr : c_ip) + row_d;
+                d.nrows2 = ai ? rc.nrowsb1 : rc.nrowsb0;
+                d.par = (row_a & 1) | ((row_d & 1) << 1);
+                if (d.nrows2 > 0) d.kind |= K2_TILE_MIRROR;
+            }
             rc.desc[slot] = d;
         }
         // the lane owns rows 16g+4c .. 16g+4c+3 of the unit: (even tile, odd tile) interleaved
@@ -554,6 +574,7 @@ __device__ __forceinline__ void k2_send_marker(const K2Ctx &cx, K2RCtx &rc, cons
     if (cx.lane == 0) {
         K2Tile d;
         d.ea = d.ed = 0; d.s_hi = d.s_lo_d = d.nrows = d.dib_a = d.dib_d = 0; d.kind = kind;
+        d.ea2 = d.ed2 = 0; d.nrows2 = 0; d.par = 0;
         rc.desc[slot] = d;
     }
     __syncwarp();
@@ -565,16 +586,22 @@ __device__ __forceinline__ void k2_send_marker(const K2Ctx &cx, K2RCtx &rc, cons
 // All eight matrix pointers of a target are formed BEFORE its stores issue: a pointer that is advanced in place right
 // after its store waits for the store to read it (write-after-read through the LSU queue, ~25 cycles per store in
 // the ncu source view; the store warps were busy 83 % of the time and the compute warps waited for free slots).
-__device__ __forceinline__ void k2_drain_pair(const double *buf, double *out, const K2Tile &d, const size_t NN, const int lane)
+// MIRROR: the targets of the mirror matrices (ea2 / ed2, matrices stepping backwards, row-alternating extra sign)
+// (the descriptor stays in shared memory -- dp -- and is read field by field: the store warps run on 56 registers)
+template <bool MIRROR>
+__device__ __forceinline__ void k2_drain_targets(const double *buf, double *out, const K2Tile *dp, const size_t NN, const int lane)
 {
-    const size_t step = 2 * NN;                                       // angle ar of the tile is matrix 2*ar further on
+    const long long step = MIRROR ? -2 * (long long)NN : 2 * (long long)NN;   // angle ar of the tile is matrix 2*ar further on (back)
+    const int nrows = MIRROR ? dp->nrows2 : dp->nrows;
+    const int s_hi = dp->s_hi, kind = dp->kind;
 #pragma unroll 1
-    for (int s = lane; s < d.s_hi; s += 32) {
+    for (int s = lane; s < s_hi; s += 32) {
         const double *sp = buf + s;
-        const bool on_a = (d.kind & K2_TILE_ASC) != 0, on_d = (d.kind & K2_TILE_DESC) != 0 && s >= d.s_lo_d;
-        double *pa = out + d.ea + s, *pd = out + d.ed - s;
-        const unsigned sa = sigma_bit(d.dib_a + s), sd = sigma_bit(d.dib_d - s);
-        if (d.nrows == K2_HT_ROWS) {                                  // all 8 loads in flight before the stores
+        const bool on_a = (kind & K2_TILE_ASC) != 0, on_d = (kind & K2_TILE_DESC) != 0 && s >= dp->s_lo_d;
+        double *pa = out + (MIRROR ? dp->ea2 : dp->ea) + s, *pd = out + (MIRROR ? dp->ed2 : dp->ed) - s;
+        unsigned sa = sigma_bit(dp->dib_a + s), sd = sigma_bit(dp->dib_d - s);
+        if (MIRROR) { const int par = dp->par; sa ^= ((unsigned)(par + s) & 1u) << 31; sd ^= ((unsigned)((par >> 1) + s) & 1u) << 31; }   // (-1)^row
+        if (nrows == K2_HT_ROWS) {                                    // all 8 loads in flight before the stores
             double v[K2_HT_ROWS];
             double *q[K2_HT_ROWS];
 #pragma unroll
@@ -596,7 +623,7 @@ __device__ __forceinline__ void k2_drain_pair(const double *buf, double *out, co
             }
         } else {
 #pragma unroll 1
-            for (int ar = 0; ar < d.nrows; ++ar) {
+            for (int ar = 0; ar < nrows; ++ar) {
                 const double v = sp[ar * K2_STG_LD];
                 if (on_a) *pa = flip(v, sa);
                 if (on_d) *pd = flip(v, sd);
@@ -604,6 +631,11 @@ __device__ __forceinline__ void k2_drain_pair(const double *buf, double *out, co
             }
         }
     }
+}
+__device__ __forceinline__ void k2_drain_pair(const double *buf, double *out, const K2Tile *dp, const size_t NN, const int lane)
+{
+    k2_drain_targets<false>(buf, out, dp, NN, lane);
+    if (dp->kind & K2_TILE_MIRROR) k2_drain_targets<true>(buf, out, dp, NN, lane);
 }
 
 // Store warp q: drains the 2-slot ring of compute warp q until the END marker.
@@ -617,9 +649,8 @@ __device__ __forceinline__ void k2_store_loop(const double *stg, const double *d
     for (unsigned t = 0;; ++t) {
         const int slot = t & 1;
         mbar_wait(full + slot, (t >> 1) & 1);                          // acquire: tile + descriptor are visible
-        const K2Tile d = desc[slot];
-        if (d.kind == K2_TILE_END_ALL) break;
-        k2_drain_pair(ring + slot * K2_HT_SIZE, out, d, NN, lane);
+        if (desc[slot].kind == K2_TILE_END_ALL) break;
+        k2_drain_pair(ring + slot * K2_HT_SIZE, out, desc + slot, NN, lane);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + slot);                      // release: the slot may be overwritten
     }
@@ -727,6 +758,7 @@ __global__ void __launch_bounds__(K2_THREADS_REAL, 1) k2_real_kernel(K2Args a)
     rc.full = bars + 2 * warp; rc.empty = bars + 2 * K2_CWARPS + 2 * warp;
     rc.tiles = 0;
     rc.NN = (size_t)p.N * p.N;
+    rc.paired = 0; rc.nrowsb0 = rc.nrowsb1 = 0; rc.e_item_b = 0;
     // hand-off between the two compute warps (w, w+4) of an SM sub-partition: see k2_cplx_kernel
     cx.krel = a.handoff - 1;
     cx.bar_me = a.handoff ? 2 + warp : 0;

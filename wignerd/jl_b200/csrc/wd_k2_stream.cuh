@@ -36,6 +36,8 @@ struct K2SArgs {
     const double *uqc;         // chunk-major copy of UQ: [mu chunk][qpad rows][K2S_LDU], zero on the pads (k2s_table_kernel)
     int qpad;                  // rows per chunk of uqc: Q rounded up to whole row blocks
     int nck0, nck1;            // mu chunks of class 0 / class 1
+    const int *pair_flag;      // device flag of k2c_pair_check_kernel (1: the batch is symmetric, beta[b] + beta[nb-1-b] = pi):
+                               // only the first half of the angles is contracted, every tile also feeds the mirror matrices
 };
 
 // Chunk-major, row-padded copy of a plan's UQ: the row block and the column rows of a mu chunk are then contiguous
@@ -80,9 +82,10 @@ __host__ __device__ inline K2SSmem k2s_smem_layout(bool half)
 
 // trig table: T[ac][kc][0|1][row(angle)][col] = w * cos|sin(mu * beta), zero on the pads
 __global__ void __launch_bounds__(256) k2s_trig_kernel(PlanDev p, const double *__restrict__ beta, long long nb,
-                                                       double *__restrict__ trig, int nck0, int nck1)
+                                                       double *__restrict__ trig, int nck0, int nck1, const int *pair_flag)
 {
     const int nck = nck0 + nck1;
+    if (pair_flag != nullptr && *reinterpret_cast<const volatile int *>(pair_flag) != 0) nb = (nb + 1) / 2;   // front half only
     const long long nac = (nb + K2_ANG - 1) / K2_ANG;
     const long long total = nac * nck * K2_ANG * K2S_KC;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -191,6 +194,9 @@ __global__ void __launch_bounds__(K2_THREADS_REAL, 1) k2_stream_kernel(K2SArgs s
     rc.full = bars + 2 * warp; rc.empty = bars + 2 * K2_CWARPS + 2 * warp;
     rc.tiles = 0;
     rc.NN = (size_t)p.N * p.N;
+    const int paired = (sa.pair_flag != nullptr && a.nb >= 2) ? *reinterpret_cast<const volatile int *>(sa.pair_flag) : 0;
+    const long long H = paired ? (a.nb + 1) / 2 : a.nb;          // angles that are contracted
+    rc.paired = paired; rc.nrowsb0 = rc.nrowsb1 = 0; rc.e_item_b = 0;
     cx.ldu = ldu; cx.ldt = 0; cx.N = p.N; cx.Q = Q; cx.i0 = p.N - Q; cx.zskip = p.zskip;
     cx.Kp = p.Kp; cx.K0p = p.K0p; cx.twoj = p.twoj;
     cx.lane = lane; cx.r = lane >> 2; cx.c = lane & 3;
@@ -200,7 +206,7 @@ __global__ void __launch_bounds__(K2_THREADS_REAL, 1) k2_stream_kernel(K2SArgs s
     const int ngroups = (Q + 15) >> 4;
     const int nrb = (ngroups + GMAX - 1) / GMAX;           // row blocks
     const int ncb = (Q + K2_CWARPS - 1) / K2_CWARPS;       // column blocks (8 columns each)
-    const long long nac = (a.nb + K2_ANG - 1) / K2_ANG;
+    const long long nac = (H + K2_ANG - 1) / K2_ANG;
     const long long ntiles = nac * nrb * ncb;
     const int nck0 = sa.nck0, nck = sa.nck0 + sa.nck1;
     unsigned gch = 0;                                      // chunks consumed so far by this CTA (ring position / phases)
@@ -211,9 +217,16 @@ __global__ void __launch_bounds__(K2_THREADS_REAL, 1) k2_stream_kernel(K2SArgs s
         const long long ac = tile / ((long long)ncb * nrb);
         cx.b0 = ac * K2_ANG;
         rc.e_item = (size_t)cx.b0 * rc.NN;
-        rc.nrows0 = (int)min(8LL, (a.nb - cx.b0 + 1) / 2);
-        rc.nrows1 = (int)min(8LL, (a.nb - cx.b0) / 2);
+        rc.nrows0 = (int)min(8LL, (H - cx.b0 + 1) / 2);
+        rc.nrows1 = (int)min(8LL, (H - cx.b0) / 2);
         rc.ntiles = rc.nrows1 > 0 ? 2 : 1;
+        if (paired) {
+            // angle b0 + ai + 2 ar has the mirror matrix nb-1-b (if that lies in the second half): a prefix of the tile's angles
+            const long long last = a.nb - 1 - H - cx.b0;          // largest angle offset whose mirror is >= H
+            rc.nrowsb0 = last >= 0 ? (int)min((long long)rc.nrows0, last / 2 + 1) : 0;
+            rc.nrowsb1 = last >= 1 ? (int)min((long long)rc.nrows1, (last - 1) / 2 + 1) : 0;
+            rc.e_item_b = (size_t)(a.nb - 1 - cx.b0) * rc.NN;
+        }
         const int g0 = rb * GMAX, gcnt = min(GMAX, ngroups - g0);
         const int qn = cb * K2_CWARPS + warp;
         const bool active = qn < Q;

@@ -219,7 +219,16 @@ __global__ void __launch_bounds__(256) k2_plain_kernel(K2Args a)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4: single elements.  One warp per tuple; lanes stride the padded mu axis.
+// K4: single elements (wignerdjmn / wignerDjmn).  One THREAD per tuple, 32 tuples per warp.
+//   * The two table rows u[m, .], u[n, .] of every tuple are L2-resident (86 MB for all 2j <= 400); the warp brings them in
+//     16 columns at a time through shared memory: per tuple one coalesced load (half a warp per row), then every thread
+//     walks its own 2 x 16 values conflict-free (row stride 33).
+//   * The reference takes one sincos per term (src/WignerD.jl:199).  Here a thread anchors (cos, sin)(mu beta) with an exact
+//     sincos(fl(mu beta)) at the start of every 16-column chunk (and at the class boundary) and steps mu -> mu + 2 inside
+//     the chunk with a rotation by 2 beta (4 multiply-adds): <= 15 rotation steps from an anchor keep the trig values
+//     within ~4e-15 of the reference's, the sum within ~1e-14.  (First version: one warp per tuple, one sin or cos per
+//     term: 6.3-6.5 ms for the 10^7 tuples of cfg-5, bound by issuing ~10^9 FP64 sin/cos -- 35 % of the measured sin()
+//     issue rate of the chip.)
 // ------------------------------------------------------------------------------------------------
 struct K4Args {
     const PlanDev *plans;     // indexed by twoj (entries with uq == nullptr are unprepared)
@@ -232,57 +241,104 @@ struct K4Args {
     int *err;                 // set to 1 on an invalid tuple
 };
 
+constexpr int K4_WARPS = 4, K4_CH = 16, K4_SEG = 2 * K4_CH + 1;
+
 template <bool CPLX>
-__global__ void __launch_bounds__(256) k4_jmn_kernel(K4Args a)
+__global__ void __launch_bounds__(K4_WARPS * 32) k4_jmn_kernel(K4Args a)
 {
-    const int lane = threadIdx.x & 31;
-    const long long wpg = (long long)gridDim.x * (blockDim.x >> 5);
-    for (long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < a.n; t += wpg) {
-        const int tj = a.twoj[t], tm = a.twom[t], tn = a.twon[t];
+    __shared__ double sSeg[K4_WARPS][32 * K4_SEG];
+    __shared__ const double *sRow[K4_WARPS][32][2];
+    __shared__ int sKp[K4_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *seg = sSeg[warp];
+    const long long ngroups = (a.n + 31) / 32;
+    const long long wpg = (long long)gridDim.x * K4_WARPS;
+    for (long long grp = (long long)blockIdx.x * K4_WARPS + warp; grp < ngroups; grp += wpg) {
+        const long long t = grp * 32 + lane;
+        const bool live = t < a.n;
+        const int tj = live ? a.twoj[t] : 0, tm = live ? a.twom[t] : 0, tn = live ? a.twon[t] : 0;
         const int kind = a.beta_kind;
         double val = 0.0;
-        bool done = false;
+        bool done = !live;
         // special co-latitudes (src/WignerD.jl:218-237); the poles do no index checks, like the reference
-        if (kind == 1) { val = (tm == tn) ? 1.0 : 0.0; done = true; }
-        else if (kind == 2) {
-            val = (tm == -tn) ? ((((tj - tn) >> 1) & 1) ? -1.0 : 1.0) : 0.0; done = true;
-        } else if (kind == 3 && ((tj + tm) & 1) == 0 && ((tj + tn) & 1) == 0) {
-            const bool jm_odd = ((tj + tm) >> 1) & 1, jn_odd = ((tj + tn) >> 1) & 1;
-            if ((jm_odd && tn == 0) || (jn_odd && tm == 0)) { val = 0.0; done = true; }
+        if (live) {
+            if (kind == 1) { val = (tm == tn) ? 1.0 : 0.0; done = true; }
+            else if (kind == 2) { val = (tm == -tn) ? ((((tj - tn) >> 1) & 1) ? -1.0 : 1.0) : 0.0; done = true; }
+            else if (kind == 3 && ((tj + tm) & 1) == 0 && ((tj + tn) & 1) == 0) {
+                const bool jm_odd = ((tj + tm) >> 1) & 1, jn_odd = ((tj + tn) >> 1) & 1;
+                if ((jm_odd && tn == 0) || (jn_odd && tm == 0)) { val = 0.0; done = true; }
+            }
         }
+        int Kp = 0, K0p = 0, c0 = 0, par = 0, sdi = 0;
+        bool flip1 = false, odd = false;
+        double beta = 0.0;
+        const double *um = nullptr, *un = nullptr;
         if (!done) {
             const bool ok = tj >= 0 && tj <= a.max_twoj && ((tj + tm) & 1) == 0 && ((tj + tn) & 1) == 0 &&
                             tm >= -tj && tm <= tj && tn >= -tj && tn <= tj;
-            if (!ok) { if (lane == 0) *a.err = 1; continue; }
-            const PlanDev p = a.plans[tj];
-            const double beta = (kind == 3) ? 1.5707963267948966 : a.beta[t];
-            const int N = p.N, i0 = N - p.Q;
-            const int i = (tm + tj) >> 1, ip = (tn + tj) >> 1;
-            const int qm = (i >= i0) ? i - i0 : (N - 1 - i) - i0;
-            const int qn = (ip >= i0) ? ip - i0 : (N - 1 - ip) - i0;
-            const bool flip1 = ((i < i0) != (ip < i0));       // one mirrored index: class 1 changes sign
-            const bool odd = (i - ip) & 1;
-            const double *um = p.uq + (size_t)qm * p.ldu, *un = p.uq + (size_t)qn * p.ldu;
-            double s0 = 0.0, s1 = 0.0;
-            // mu and w of column kp are recomputed from the index (same arithmetic as k1_eig_kernel) instead of being
-            // read: the kernel is bound by L2 reads of the two table rows
-            const int K = p.Q, c0 = (K - 1) & 1, par = p.twoj & 1;
-            for (int kp = lane; kp < p.Kp; kp += 32) {
-                const bool cls1 = kp >= p.K0p;
-                const int t = cls1 ? kp - p.K0p : kp;
-                if (t >= (cls1 ? p.K1 : p.K0)) continue;             // pad column
-                const int kappa = (cls1 ? (c0 ^ 1) : c0) + 2 * t;
-                const double mu = 0.5 * (double)(2 * kappa + par);
-                const double tr = odd ? sin(mu * beta) : cos(mu * beta);     // (warp-uniform choice: one function, not sincos)
-                const double g = ((kappa | par) ? 2.0 : 1.0) * tr * (um[kp] * un[kp]);
-                if (cls1) s1 += g; else s0 += g;
+            const PlanDev *pp = ok ? a.plans + tj : nullptr;
+            if (!ok || pp->uq == nullptr) { *a.err = 1; done = true; }
+            else {
+                const int N = pp->N, Q = pp->Q, i0 = N - Q, ldu = pp->ldu;
+                const int i = (tm + tj) >> 1, ip = (tn + tj) >> 1;
+                const int qm = (i >= i0) ? i - i0 : (N - 1 - i) - i0;
+                const int qn = (ip >= i0) ? ip - i0 : (N - 1 - ip) - i0;
+                flip1 = ((i < i0) != (ip < i0));             // one mirrored index: class 1 changes sign
+                odd = (i - ip) & 1;
+                sdi = i - ip;
+                um = pp->uq + (size_t)qm * ldu; un = pp->uq + (size_t)qn * ldu;
+                Kp = pp->Kp; K0p = pp->K0p;
+                c0 = (Q - 1) & 1; par = tj & 1;
+                beta = (kind == 3) ? 1.5707963267948966 : a.beta[t];
             }
-            double x = flip1 ? (s0 - s1) : (s0 + s1);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-            val = flip(x, sigma_bit(i - ip));
         }
-        if (lane == 0) {
+        sRow[warp][lane][0] = um; sRow[warp][lane][1] = un;
+        sKp[warp][lane] = done ? 0 : Kp;
+        const int kmax = __reduce_max_sync(0xffffffffu, done ? 0 : Kp);
+        double s2, c2;
+        sincos(2.0 * beta, &s2, &c2);                         // rotation step mu -> mu + 2 inside a class
+        double acc0 = 0.0, acc1 = 0.0;
+        __syncwarp();
+#pragma unroll 1
+        for (int kb = 0; kb < kmax; kb += K4_CH) {
+            // stage columns kb .. kb+15 of both rows of the 32 tuples: lanes 0-15 row m, lanes 16-31 row n of tuple tt
+#pragma unroll 8
+            for (int tt = 0; tt < 32; ++tt) {
+                const int col = kb + (lane & 15);
+                double v = 0.0;
+                if (col < sKp[warp][tt]) v = sRow[warp][tt][lane >> 4][col];
+                seg[tt * K4_SEG + lane] = v;
+            }
+            __syncwarp();
+            if (kb < (done ? 0 : Kp)) {
+                const double *my = seg + lane * K4_SEG;
+                // anchor: exact sincos(fl(mu * beta)) like src/WignerD.jl:199; mu of padded column kp: class 0 mu = c0 + 2 kp (+1/2),
+                // class 1 (kp >= K0p) mu = (c0^1) + 2 (kp - K0p) (+1/2)
+                auto kappa_of = [&](const int kp) { return (kp >= K0p) ? (c0 ^ 1) + 2 * (kp - K0p) : c0 + 2 * kp; };
+                auto mu_of = [&](const int kp) { return 0.5 * (double)(2 * kappa_of(kp) + par); };
+                double sn, cs;
+                sincos(mu_of(kb) * beta, &sn, &cs);
+                const int kend = min(K4_CH, Kp - kb);
+#pragma unroll 4
+                for (int ii = 0; ii < kend; ++ii) {
+                    const int kp = kb + ii;
+                    if (kp == K0p && ii > 0) sincos(mu_of(kp) * beta, &sn, &cs);       // class boundary inside the chunk
+                    const double g = my[ii] * my[K4_CH + ii];
+                    const double w = (kappa_of(kp) | par) ? 2.0 : 1.0;                  // mu = 0 has weight 1
+                    const double term = (w * (odd ? sn : cs)) * g;
+                    if (kp >= K0p) acc1 += term; else acc0 += term;
+                    const double cn = cs * c2 - sn * s2;
+                    sn = fma(sn, c2, cs * s2);
+                    cs = cn;
+                }
+            }
+            __syncwarp();
+        }
+        if (!done) {
+            const double x = flip1 ? (acc0 - acc1) : (acc0 + acc1);
+            val = flip(x, sigma_bit(sdi));
+        }
+        if (live) {
             if (!CPLX) a.out[t] = val;
             else {
                 const double m = 0.5 * (double)tm, n = 0.5 * (double)tn;
@@ -291,6 +347,7 @@ __global__ void __launch_bounds__(256) k4_jmn_kernel(K4Args a)
                 reinterpret_cast<double2 *>(a.out)[t] = make_double2(val * c, val * s);
             }
         }
+        __syncwarp();
     }
 }
 
