@@ -894,9 +894,10 @@ int jmn_common(wd_handle_t h, const int32_t *twoj, const int32_t *twom, const in
         a.twoj = d_tj; a.twom = d_tm; a.twon = d_tn;
         a.beta = d_b; a.alpha = d_a; a.gamma = d_g;
         a.n = n; a.beta_kind = beta_kind; a.out = d_out; a.err = h->d_flag;
-        const int blocks = (int)std::min<long long>((n + 32 * K4_WARPS - 1) / (32 * K4_WARPS), (long long)h->num_sms * 12);
-        if (cplx) k4_jmn_kernel<true><<<blocks, K4_WARPS * 32, 0, h->stream>>>(a);
-        else k4_jmn_kernel<false><<<blocks, K4_WARPS * 32, 0, h->stream>>>(a);
+        const int per_block = K4_THREADS / K4_G;
+        const int blocks = (int)std::min<long long>((n + per_block - 1) / per_block, (long long)h->num_sms * 16);
+        if (cplx) k4_jmn_kernel<true><<<blocks, K4_THREADS, 0, h->stream>>>(a);
+        else k4_jmn_kernel<false><<<blocks, K4_THREADS, 0, h->stream>>>(a);
         h->launches++;
         if (mem == WD_MEM_HOST) cudaMemcpyAsync(stage ? (void *)(stage + stage_out_off) : (void *)out, d_out, osz, cudaMemcpyDeviceToHost, h->stream);
         cudaMemcpyAsync(hflag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream);

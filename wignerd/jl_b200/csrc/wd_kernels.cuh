@@ -219,16 +219,15 @@ __global__ void __launch_bounds__(256) k2_plain_kernel(K2Args a)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4: single elements (wignerdjmn / wignerDjmn).  One THREAD per tuple, 32 tuples per warp.
-//   * The two table rows u[m, .], u[n, .] of every tuple are L2-resident (86 MB for all 2j <= 400); the warp brings them in
-//     16 columns at a time through shared memory: per tuple one coalesced load (half a warp per row), then every thread
-//     walks its own 2 x 16 values conflict-free (row stride 33).
-//   * The reference takes one sincos per term (src/WignerD.jl:199).  Here a thread anchors (cos, sin)(mu beta) with an exact
-//     sincos(fl(mu beta)) at the start of every 16-column chunk (and at the class boundary) and steps mu -> mu + 2 inside
-//     the chunk with a rotation by 2 beta (4 multiply-adds): <= 15 rotation steps from an anchor keep the trig values
-//     within ~4e-15 of the reference's, the sum within ~1e-14.  (First version: one warp per tuple, one sin or cos per
-//     term: 6.3-6.5 ms for the 10^7 tuples of cfg-5, bound by issuing ~10^9 FP64 sin/cos -- 35 % of the measured sin()
-//     issue rate of the chip.)
+// K4: single elements (wignerdjmn / wignerDjmn).  EIGHT lanes per tuple, four tuples per warp.
+//   * Lane g of a group takes the columns kp = g, g + 8, ... of each eigenvector class of the two L2-resident table rows
+//     u[m, .], u[n, .] (coalesced 64-byte pieces), so that its angle advances by a FIXED step from term to term:
+//     mu -> mu + 16.  The reference takes one sincos per term (src/WignerD.jl:199); here a lane anchors (cos, sin)(mu beta)
+//     with an exact sincos(fl(mu beta)) at its first column of each class (and again every 16 steps) and advances it
+//     with a rotation by 16 beta (4 multiply-adds) in between: the trig values stay within ~4e-15 of the reference's.
+//   * Tried: one warp per tuple with one sin or cos per term (round 1): 6.3-6.5 ms for the 10^7 tuples of cfg-5, i.e.
+//     35 % of the chip's measured FP64 sin() issue rate; one THREAD per tuple with the rows staged through shared memory:
+//     7.2 ms (32 tuples of different j per warp: every warp runs to the longest of them).
 // ------------------------------------------------------------------------------------------------
 struct K4Args {
     const PlanDev *plans;     // indexed by twoj (entries with uq == nullptr are unprepared)
@@ -241,20 +240,17 @@ struct K4Args {
     int *err;                 // set to 1 on an invalid tuple
 };
 
-constexpr int K4_WARPS = 4, K4_CH = 16, K4_SEG = 2 * K4_CH + 1;
+constexpr int K4_G = 8;                     // lanes per tuple
+constexpr int K4_THREADS = 256;
 
 template <bool CPLX>
-__global__ void __launch_bounds__(K4_WARPS * 32) k4_jmn_kernel(K4Args a)
+__global__ void __launch_bounds__(K4_THREADS) k4_jmn_kernel(K4Args a)
 {
-    __shared__ double sSeg[K4_WARPS][32 * K4_SEG];
-    __shared__ const double *sRow[K4_WARPS][32][2];
-    __shared__ int sKp[K4_WARPS][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *seg = sSeg[warp];
-    const long long ngroups = (a.n + 31) / 32;
-    const long long wpg = (long long)gridDim.x * K4_WARPS;
-    for (long long grp = (long long)blockIdx.x * K4_WARPS + warp; grp < ngroups; grp += wpg) {
-        const long long t = grp * 32 + lane;
+    const int lane = threadIdx.x & 31, g = lane & (K4_G - 1);
+    const long long slots = (long long)gridDim.x * (K4_THREADS / K4_G);
+    for (long long t = (long long)blockIdx.x * (K4_THREADS / K4_G) + (threadIdx.x / K4_G);; t += slots) {
+        // whole warps leave together (the shuffles below are warp-wide)
+        if (__all_sync(0xffffffffu, t >= a.n)) break;
         const bool live = t < a.n;
         const int tj = live ? a.twoj[t] : 0, tm = live ? a.twom[t] : 0, tn = live ? a.twon[t] : 0;
         const int kind = a.beta_kind;
@@ -269,76 +265,56 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_jmn_kernel(K4Args a)
                 if ((jm_odd && tn == 0) || (jn_odd && tm == 0)) { val = 0.0; done = true; }
             }
         }
-        int Kp = 0, K0p = 0, c0 = 0, par = 0, sdi = 0;
-        bool flip1 = false, odd = false;
-        double beta = 0.0;
-        const double *um = nullptr, *un = nullptr;
+        double acc0 = 0.0, acc1 = 0.0;
+        bool flip1 = false;
+        int sdi = 0;
         if (!done) {
             const bool ok = tj >= 0 && tj <= a.max_twoj && ((tj + tm) & 1) == 0 && ((tj + tn) & 1) == 0 &&
                             tm >= -tj && tm <= tj && tn >= -tj && tn <= tj;
-            const PlanDev *pp = ok ? a.plans + tj : nullptr;
-            if (!ok || pp->uq == nullptr) { *a.err = 1; done = true; }
+            const PlanDev *pp = a.plans + (ok ? tj : 0);
+            const double *uq = ok ? pp->uq : nullptr;
+            if (uq == nullptr) { if (g == 0) *a.err = 1; done = true; }
             else {
-                const int N = pp->N, Q = pp->Q, i0 = N - Q, ldu = pp->ldu;
+                const int N = tj + 1, Q = (N + 1) >> 1, i0 = N - Q, ldu = pp->ldu, K0p = pp->K0p, Kp = pp->Kp;
                 const int i = (tm + tj) >> 1, ip = (tn + tj) >> 1;
                 const int qm = (i >= i0) ? i - i0 : (N - 1 - i) - i0;
                 const int qn = (ip >= i0) ? ip - i0 : (N - 1 - ip) - i0;
                 flip1 = ((i < i0) != (ip < i0));             // one mirrored index: class 1 changes sign
-                odd = (i - ip) & 1;
+                const bool odd = (i - ip) & 1;
                 sdi = i - ip;
-                um = pp->uq + (size_t)qm * ldu; un = pp->uq + (size_t)qn * ldu;
-                Kp = pp->Kp; K0p = pp->K0p;
-                c0 = (Q - 1) & 1; par = tj & 1;
-                beta = (kind == 3) ? 1.5707963267948966 : a.beta[t];
-            }
-        }
-        sRow[warp][lane][0] = um; sRow[warp][lane][1] = un;
-        sKp[warp][lane] = done ? 0 : Kp;
-        const int kmax = __reduce_max_sync(0xffffffffu, done ? 0 : Kp);
-        double s2, c2;
-        sincos(2.0 * beta, &s2, &c2);                         // rotation step mu -> mu + 2 inside a class
-        double acc0 = 0.0, acc1 = 0.0;
-        __syncwarp();
+                const double *um = uq + (size_t)qm * ldu, *un = uq + (size_t)qn * ldu;
+                const int c0 = (Q - 1) & 1, par = tj & 1;
+                const double beta = (kind == 3) ? 1.5707963267948966 : a.beta[t];
+                double s2, c2;
+                sincos((double)(2 * K4_G) * beta, &s2, &c2);             // mu advances by 2 per column of a class, 16 per lane step
+#pragma unroll
+                for (int cls = 0; cls < 2; ++cls) {
+                    const int kbeg = cls ? K0p : 0, kend = cls ? Kp : K0p;     // (pad columns hold zeros)
+                    const int kappa0 = (cls ? (c0 ^ 1) : c0) + 2 * g;          // mu of column kbeg + g: kappa0 (+ 1/2)
+                    double acc = 0.0, sn = 0.0, cs = 1.0;
+                    int it = 0;
 #pragma unroll 1
-        for (int kb = 0; kb < kmax; kb += K4_CH) {
-            // stage columns kb .. kb+15 of both rows of the 32 tuples: lanes 0-15 row m, lanes 16-31 row n of tuple tt
-#pragma unroll 8
-            for (int tt = 0; tt < 32; ++tt) {
-                const int col = kb + (lane & 15);
-                double v = 0.0;
-                if (col < sKp[warp][tt]) v = sRow[warp][tt][lane >> 4][col];
-                seg[tt * K4_SEG + lane] = v;
-            }
-            __syncwarp();
-            if (kb < (done ? 0 : Kp)) {
-                const double *my = seg + lane * K4_SEG;
-                // anchor: exact sincos(fl(mu * beta)) like src/WignerD.jl:199; mu of padded column kp: class 0 mu = c0 + 2 kp (+1/2),
-                // class 1 (kp >= K0p) mu = (c0^1) + 2 (kp - K0p) (+1/2)
-                auto kappa_of = [&](const int kp) { return (kp >= K0p) ? (c0 ^ 1) + 2 * (kp - K0p) : c0 + 2 * kp; };
-                auto mu_of = [&](const int kp) { return 0.5 * (double)(2 * kappa_of(kp) + par); };
-                double sn, cs;
-                sincos(mu_of(kb) * beta, &sn, &cs);
-                const int kend = min(K4_CH, Kp - kb);
-#pragma unroll 4
-                for (int ii = 0; ii < kend; ++ii) {
-                    const int kp = kb + ii;
-                    if (kp == K0p && ii > 0) sincos(mu_of(kp) * beta, &sn, &cs);       // class boundary inside the chunk
-                    const double g = my[ii] * my[K4_CH + ii];
-                    const double w = (kappa_of(kp) | par) ? 2.0 : 1.0;                  // mu = 0 has weight 1
-                    const double term = (w * (odd ? sn : cs)) * g;
-                    if (kp >= K0p) acc1 += term; else acc0 += term;
-                    const double cn = cs * c2 - sn * s2;
-                    sn = fma(sn, c2, cs * s2);
-                    cs = cn;
+                    for (int kp = kbeg + g; kp < kend; kp += K4_G, ++it) {
+                        const int kappa = kappa0 + 2 * K4_G * it;
+                        if ((it & 15) == 0) sincos(0.5 * (double)(2 * kappa + par) * beta, &sn, &cs);   // exact anchor, like :199
+                        const double gg = um[kp] * un[kp];
+                        const double w = (kappa | par) ? 2.0 : 1.0;             // mu = 0 has weight 1
+                        acc = fma(w * (odd ? sn : cs), gg, acc);
+                        const double cn = cs * c2 - sn * s2;
+                        sn = fma(sn, c2, cs * s2);
+                        cs = cn;
+                    }
+                    if (cls) acc1 = acc; else acc0 = acc;
                 }
             }
-            __syncwarp();
         }
-        if (!done) {
-            const double x = flip1 ? (acc0 - acc1) : (acc0 + acc1);
-            val = flip(x, sigma_bit(sdi));
+#pragma unroll
+        for (int o = K4_G / 2; o > 0; o >>= 1) {
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+            acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
         }
-        if (live) {
+        if (live && g == 0) {
+            if (!done) val = flip(flip1 ? (acc0 - acc1) : (acc0 + acc1), sigma_bit(sdi));
             if (!CPLX) a.out[t] = val;
             else {
                 const double m = 0.5 * (double)tm, n = 0.5 * (double)tn;
@@ -347,7 +323,6 @@ __global__ void __launch_bounds__(K4_WARPS * 32) k4_jmn_kernel(K4Args a)
                 reinterpret_cast<double2 *>(a.out)[t] = make_double2(val * c, val * s);
             }
         }
-        __syncwarp();
     }
 }
 
