@@ -302,6 +302,15 @@ def pinned_empty(ctx, shape, dtype):
         return None
 
 
+def release_pinned(ctx):
+    """give pinned host blocks back to the OS (torch's caching host allocator keeps them): 8 ranks x (32 + 16 + ...) GB otherwise"""
+    try:
+        ctx.torch.cuda.synchronize()
+        ctx.torch._C._host_emptyCache()
+    except Exception:
+        pass
+
+
 def fp64_peaks(ctx):
     """FP64 denominators measured in THIS run (MEASURED_PEAKS.json has none): DMMA / DFMA register loops, cuBLAS DGEMM"""
     torch, eng = ctx.torch, ctx.eng
@@ -337,7 +346,8 @@ def rooflines(ctx, twoj, nb, ms_rank, cplx, kernel, traffic):
     bytes_alg = nb * N * N * (16 if cplx else 8)
     t = ms_rank * 1e-3
     hbm = {"bound": "hbm", "achieved": bytes_alg / t / 1e9, "peak": peak, "unit": "GB/s", "frac": bytes_alg / t / 1e9 / peak,
-           "traffic": traffic, "peak_source": peak_src, "kernel": kernel, "algorithmic_bytes_per_launch": bytes_alg}
+           "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu capture of a shorter launch, scaled)" if traffic else None,
+           "peak_source": peak_src, "kernel": kernel, "algorithmic_bytes_per_launch": bytes_alg}
     res = {"roofline_hbm": hbm, "roofline": hbm}
     p64 = ctx.fp64.get("peak_tflops")
     if p64:
@@ -351,6 +361,8 @@ def rooflines(ctx, twoj, nb, ms_rank, cplx, kernel, traffic):
 
 
 def traffic_of(name):
+    """DRAM bytes (read + write) of the config's dominant kernel per launch, FROM profiles/traffic.json: an ncu --set full
+    capture of a shorter launch of the same kernel scaled to the benched batch (see its _note), not a live measurement"""
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         t = json.load(open(tp)).get(name)
@@ -377,6 +389,7 @@ def bench_matrices(ctx, name, cfg, steps, warmup, grid="symmetric", e2e=True, pa
     else:
         if grid == "symmetric":
             beta = symmetric_betas(ctx, nb)
+            nb_nominal, nb = nb, beta.numel()             # the 16-aligned symmetric shards differ by up to 32 angles between ranks
             inputs = "beta = the rank's symmetric shard (slab of the first half + its mirror image) of linspace(0, pi, n_gpus * angles_per_gpu)"
         else:
             gen = torch.Generator(device=ctx.dev).manual_seed(1 + ctx.rank)
@@ -384,7 +397,8 @@ def bench_matrices(ctx, name, cfg, steps, warmup, grid="symmetric", e2e=True, pa
             inputs = "beta ~ U[0, pi), torch.Generator(cuda).manual_seed(1 + rank) (the generic-grid variant of SURVEY 8(d))"
         out = torch.empty((nb, N, N), dtype=torch.float64, device=ctx.dev)
         step = lambda: eng.wignerd_batch(jv, beta, out=out)                     # noqa: E731
-    elems = nb * N * N
+    elems = nb * N * N                                    # this rank's
+    elems_all = (nb_nominal if (not cplx and grid == "symmetric") else nb) * N * N * ctx.world
     bytes_out = elems * (16 if cplx else 8)
     sampler = ClockSampler(ctx.local) if (clocks and ctx.rank == 0) else None
     for _ in range(warmup):
@@ -402,12 +416,12 @@ def bench_matrices(ctx, name, cfg, steps, warmup, grid="symmetric", e2e=True, pa
         kernel = "k2_stream_kernel"
     else:
         kernel = "k2_col_kernel (paired)" if (grid == "symmetric" and 5 <= twoj <= 200 and nb >= 32) else "k2_real_kernel"
-    rec = {"ms_per_step": ms_max, "value": elems * ctx.world / (ms_max * 1e-3), "unit": "elements/s", "steps": steps,
+    rec = {"ms_per_step": ms_max, "value": elems_all / (ms_max * 1e-3), "unit": "elements/s", "steps": steps,
            "gpu_launches": int(launches), "angles_per_gpu": nb, "twoj": twoj, "inputs": inputs,
            "l2": ("outputs (>= 16 GB per step) far exceed the 126 MB L2; no flush needed" if bytes_out > 4 * 126e6 else
                   "L2-RESIDENT timing: the step's output fits in the 126 MB L2 and is rewritten every step without a flush "
                   "(CPU-runnable sanity config, launch/latency bound; not a bandwidth claim)")}
-    rec.update(rooflines(ctx, twoj, nb, ms_rank, cplx, kernel, traffic_of(name)))
+    rec.update(rooflines(ctx, twoj, nb, ms_rank, cplx, kernel, traffic_of(name if (cplx or grid == "symmetric") else name + "_random_grid")))
     if clk is not None:
         rec["clocks"] = clk
     del out
@@ -449,6 +463,7 @@ def bench_matrices(ctx, name, cfg, steps, warmup, grid="symmetric", e2e=True, pa
                                    "note": "destination = pageable numpy memory (pages touched beforehand)"}
             del pg
         del h_out
+        release_pinned(ctx)
     return rec
 
 
@@ -457,8 +472,9 @@ def bench_multi(ctx, name, cfg, steps, warmup, e2e=True):
     (0.74 TB per 512 angles) is consumed in place: each j overwrites one reusable buffer -- the ring buffer of SURVEY 7.7."""
     torch, eng = ctx.torch, ctx.eng
     jmax = cfg["twoj"] // 2
-    nb = max(16, cfg["nb"] // ctx.world)
-    beta = symmetric_betas(ctx, nb)
+    nb_nominal = max(16, cfg["nb"] // ctx.world)
+    beta = symmetric_betas(ctx, nb_nominal)
+    nb = beta.numel()
     js = list(range(0, jmax + 1))
     buf = torch.empty(nb * (2 * jmax + 1) ** 2, dtype=torch.float64, device=ctx.dev)
     offsets = np.zeros(len(js), dtype=np.int64)
@@ -477,7 +493,8 @@ def bench_multi(ctx, name, cfg, steps, warmup, e2e=True):
     fa = 2.0 * nb * sum((j + 1) ** 3 for j in js)
     t = ms_rank * 1e-3
     peak, peak_src = ctx.hbm_peak
-    rec = {"ms_per_step": ms_max, "value": elems * ctx.world / (ms_max * 1e-3), "unit": "elements/s", "steps": steps,
+    elems_all = nb_nominal * ctx.world * sum((2 * j + 1) ** 2 for j in js)
+    rec = {"ms_per_step": ms_max, "value": elems_all / (ms_max * 1e-3), "unit": "elements/s", "steps": steps,
            "gpu_launches": int(launches), "angles_per_gpu": nb, "j_list": f"0..{jmax}", "prepare_all_j_s": prep_s,
            "inputs": "beta = the rank's symmetric shard of linspace(0, pi, 4096)",
            "l2": "every j writes nb*(2j+1)^2*8 bytes into one reused buffer (4.3 GB at j=512, 512 angles): outputs exceed the L2 "
@@ -505,6 +522,7 @@ def bench_multi(ctx, name, cfg, steps, warmup, e2e=True):
                       "note": "wd_d_multi with HOST buffers on a 32-angle slice of the rank's grid, every j delivered to a reused pinned "
                               "buffer: PCIe-bound"}
         del hbuf
+        release_pinned(ctx)
     return rec
 
 
@@ -513,11 +531,12 @@ def bench_rotate(ctx, steps, warmup):
     4096 / N rotations -- wd_rotate_sh works from the eigenvectors (two tensor-core GEMMs per l), no d matrix is formed"""
     torch, eng = ctx.torch, ctx.eng
     lmax = 512
-    nb = max(16, 4096 // ctx.world)
+    nb_nominal = max(16, 4096 // ctx.world)
     L2 = (lmax + 1) ** 2
     gen = torch.Generator(device=ctx.dev).manual_seed(4 + ctx.rank)
     alm = torch.complex(torch.randn(L2, dtype=torch.float64, device=ctx.dev, generator=gen), torch.randn(L2, dtype=torch.float64, device=ctx.dev, generator=gen))
-    beta = symmetric_betas(ctx, nb)
+    beta = symmetric_betas(ctx, nb_nominal)
+    nb = beta.numel()
     alpha = torch.rand(nb, dtype=torch.float64, device=ctx.dev, generator=gen) * (2 * np.pi)
     gamma = torch.rand(nb, dtype=torch.float64, device=ctx.dev, generator=gen) * (2 * np.pi)
     out = torch.empty((nb, L2), dtype=torch.complex128, device=ctx.dev)
@@ -531,9 +550,9 @@ def bench_rotate(ctx, steps, warmup):
     flops = 8.0 * nb * sum((2 * l + 1) ** 2 for l in range(lmax + 1))        # two N x N real x (nb complex) products per l
     d_elems = nb * sum((2 * l + 1) ** 2 for l in range(lmax + 1))            # the D-matrix elements this call stands for
     t = ms_rank * 1e-3
-    rec = {"ms_per_step": ms_max, "value": nb * L2 * ctx.world / (ms_max * 1e-3), "unit": "rotated coefficients/s", "steps": steps,
+    rec = {"ms_per_step": ms_max, "value": nb_nominal * L2 * ctx.world / (ms_max * 1e-3), "unit": "rotated coefficients/s", "steps": steps,
            "gpu_launches": int(launches), "rotations_per_gpu": nb, "lmax": lmax,
-           "equivalent_d_elements_per_s": d_elems * ctx.world / (ms_max * 1e-3),
+           "equivalent_d_elements_per_s": d_elems / nb * nb_nominal * ctx.world / (ms_max * 1e-3),
            "note": "the same rotations through the matrices would need every d^l(beta) of cfg4 (5.9 TB at 4096 angles); "
                    "equivalent_d_elements_per_s counts the D elements that were never formed"}
     p64 = ctx.fp64.get("peak_tflops")
@@ -553,6 +572,7 @@ def bench_rotate(ctx, steps, warmup):
                       "kernel_share_of_e2e": (ms_rank * 1e-3 * ne / nb) / dt_rank,
                       "note": "wd_rotate_sh with HOST buffers (coefficients and angles in, rotated coefficients out)"}
         del ho
+        release_pinned(ctx)
     return rec
 
 
@@ -597,6 +617,8 @@ def bench_jmn(ctx, name, cfg, steps, warmup, e2e=True):
         dt_max, _ = wall_time(ctx, lambda: eng.wignerdjmn_batch(h[0].numpy(), h[1].numpy(), h[2].numpy(), h[3].numpy(), out=ho.numpy()), 3, 1)
         rec["e2e"] = {"value": n * ctx.world / dt_max, "unit": "tuples/s", "h2d_bytes_per_step": n * 20, "d2h_bytes_per_step": n * 8,
                       "steps": 3, "note": "wd_djmn_batch with pinned HOST buffers"}
+        del h, ho
+        release_pinned(ctx)
     return rec
 
 
@@ -700,6 +722,7 @@ def host_copy_ceiling(ctx):
         dt_max = ctx.allmax(dt)
         del d, h
         torch.cuda.empty_cache()
+        release_pinned(ctx)
         cpus = sorted(os.sched_getaffinity(0))
         return {"d2h_gbs_per_rank": n * 8 / dt / 1e9, "d2h_gbs_aggregate": n * 8 * ctx.world / dt_max / 1e9,
                 "host_cpus_visible": len(cpus),

@@ -399,10 +399,10 @@ def test_empty_and_single_batches(engine):
 
 
 def test_large_and_special_float_angles(engine):
-    # |mu*beta| ~ 1e7: both sides form fl(mu*beta) and call a full-range sincos, so they still agree
+    # |mu*beta| ~ 1e7: both sides form fl(mu*beta) and call a full-range sincos, so they still agree to the north_star tolerance
     for beta in (1.0e6, -3.3e5, 12345.678):
         for j in (2, 10.5):
-            assert np.abs(engine.wignerd_batch(j, [beta])[0] - o.wignerd_batch(j, [beta])[0]).max() < 1e-9
+            assert np.abs(engine.wignerd_batch(j, [beta])[0] - o.wignerd_batch(j, [beta])[0]).max() < TOL
     d = engine.wignerd_batch(2, np.array([np.nan, np.inf, 0.5]))
     assert np.isnan(d[0]).all() and np.isnan(d[1]).all() and np.isfinite(d[2]).all()
     assert np.abs(engine.wignerd(2, 0.0) - np.eye(5)).max() < 1e-15

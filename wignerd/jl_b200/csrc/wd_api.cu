@@ -145,6 +145,7 @@ struct wd_handle_s {
     bool attr_set_real[2] = {false, false};
     int *d_pair = nullptr;            // ring of device flags written by k2c_pair_check_kernel (one per call in flight)
     unsigned pair_idx = 0;
+    const int *shared_pair_flag = nullptr;   // wd_d_multi: ONE symmetry check of the angle grid (at the tightest tolerance) for all j
     // host-path workspace, kept across calls (grow-only): angle vectors and two output slabs + their events
     double *ws_ang = nullptr, *ws_slab[2] = {nullptr, nullptr};
     size_t ws_ang_bytes = 0, ws_slab_bytes[2] = {0, 0};
@@ -346,6 +347,16 @@ constexpr int kPairRing = 64;
 // when |beta[b] + beta[nb-1-b] - pi| <= tol for every b; |d d/d beta| <= j bounds the extra error of the mirror matrix by
 // j * tol <= 5e-13 (2e-13 up to j = 100; a linspace grid deviates by <= 8e-16).
 double pair_tol(int twoj) { return std::min(2e-15, 5e-13 / (double)std::max(1, twoj / 2)); }
+
+// the device flag that says whether beta[0..nb) is symmetric about pi/2: the one wd_d_multi made for the whole call, or a fresh check
+const int *pair_flag_for(wd_handle_t h, const double *beta, long long nb, int twoj)
+{
+    if (h->shared_pair_flag) return h->shared_pair_flag;
+    int *flag = h->d_pair + (h->pair_idx++ % kPairRing);
+    k2c_pair_check_kernel<<<1, 1024, 0, h->stream>>>(beta, nb, pair_tol(twoj), flag);
+    h->launches++;
+    return flag;
+}
 bool col_fits(wd_handle_t h, const PlanDev &p, size_t *bytes)
 {
     const K2CSmem L = k2c_smem_layout(p.Q, p.Kp, p.ldu, p.N);
@@ -388,11 +399,8 @@ int launch_col(wd_handle_t h, const K2Args &a, size_t smem, int mode, const int 
     }
     // beta <-> pi - beta pairing: decided on the device, no host round trip (pair_tol)
     if (mode != 2) {
-        int *flag = h->d_pair + (h->pair_idx++ % kPairRing);
-        k2c_pair_check_kernel<<<1, 1024, 0, h->stream>>>(a.beta, a.nb, pair_tol(a.p.twoj), flag);
-        h->launches++;
-        c.pair_flag = flag;
-        if (flag_out) *flag_out = flag;
+        c.pair_flag = pair_flag_for(h, a.beta, a.nb, a.p.twoj);
+        if (flag_out) *flag_out = c.pair_flag;
     }
     const long long nch = (a.nb + K2C_ANG - 1) / K2C_ANG;
     const long long G = h->num_sms;
@@ -470,12 +478,7 @@ int launch_stream(wd_handle_t h, const Plan &cpl, const K2Args &a)
         sa.uqc = pl.uqc; sa.qpad = pl.uqc_qpad;
         // symmetric grids: pairing, decided on the device (only when the batch is not cut into slabs)
         sa.pair_flag = nullptr;
-        if (h->pairing && nac_all <= nac_cap && a.nb >= 32) {
-            int *flag = h->d_pair + (h->pair_idx++ % kPairRing);
-            k2c_pair_check_kernel<<<1, 1024, 0, h->stream>>>(a.beta, a.nb, pair_tol(a.p.twoj), flag);
-            h->launches++;
-            sa.pair_flag = flag;
-        }
+        if (h->pairing && nac_all <= nac_cap && a.nb >= 32) sa.pair_flag = pair_flag_for(h, a.beta, a.nb, a.p.twoj);
         const size_t ntrig = (size_t)nac * nck * K2S_TRIG_TILE;
         double *trig = nullptr;
         if (h->pool) CU(cudaMallocFromPoolAsync(&trig, ntrig * sizeof(double), h->pool, h->stream));
@@ -495,6 +498,23 @@ int launch_stream(wd_handle_t h, const Plan &cpl, const K2Args &a)
         if (e != cudaSuccess) return fail(WD_ERR_CUDA, "streaming kernel launch failed: %s", cudaGetErrorString(e));
     }
     return WD_OK;
+}
+
+// D[b][n][m] = d[b][n][m] * cis(-(m alpha_b + n gamma_b)): the phase loop of wignerD! (src/WignerD.jl:338-340), one element per thread
+__global__ void __launch_bounds__(256) phase_kernel(const double *__restrict__ d, const double *__restrict__ alpha, const double *__restrict__ gamma,
+                                                    long long nb, int twoj, double2 *__restrict__ D)
+{
+    const int N = twoj + 1;
+    const long long NN = (long long)N * N, total = nb * NN;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e / NN;
+        const int r = (int)(e - b * NN), row = r % N, col = r / N;
+        const double m = 0.5 * (double)(2 * row - twoj), n = 0.5 * (double)(2 * col - twoj);
+        double s, c;
+        sincos(-(m * alpha[b] + n * gamma[b]), &s, &c);
+        const double v = d[e];
+        D[e] = make_double2(v * c, v * s);
+    }
 }
 
 // d (or D) for nb generic angles, all pointers on the device.
@@ -557,6 +577,33 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
     if (use_dmma) return half ? launch_cplx<true>(h, a, smem) : launch_cplx<false>(h, a, smem);
     // real d for a table that does not fit in shared memory: the streaming DMMA kernel
     if (!cplx && !equator && variant != 1) return half ? launch_stream<true>(h, pl, a) : launch_stream<false>(h, pl, a);
+    if (cplx && !equator && variant != 1) {
+        // complex D beyond the resident kernel (2j > 223): real d of a slab of angles through the streaming DMMA kernel into a
+        // temporary, then one pass that applies cis(-(m alpha + n gamma)) exactly as src/WignerD.jl:339 does (the reference's own
+        // two-step form).  The phase pass moves 24 bytes per element; at j = 512 that is a third of the contraction's time,
+        // against the FP64-ALU kernel's O(N^3) multiply-adds (~20 x slower than the tensor path).
+        const size_t per = (size_t)pl.dev.N * pl.dev.N;
+        const long long slab = std::max<long long>(K2_ANG, std::min<long long>(nb, (((long long)1 << 30) / (long long)(per * sizeof(double))) / K2_ANG * K2_ANG));
+        double *tmp = nullptr;
+        if (h->pool) CU(cudaMallocFromPoolAsync(&tmp, (size_t)slab * per * sizeof(double), h->pool, h->stream));
+        else CU(cudaMallocAsync(&tmp, (size_t)slab * per * sizeof(double), h->stream));
+        int rc = WD_OK;
+        for (long long b0 = 0; b0 < nb && rc == WD_OK; b0 += slab) {
+            const long long cnt = std::min(slab, nb - b0);
+            K2Args s = a;
+            s.beta = beta + b0; s.nb = cnt; s.out = tmp; s.alpha = nullptr; s.gamma = nullptr;
+            rc = half ? launch_stream<true>(h, pl, s) : launch_stream<false>(h, pl, s);
+            if (rc) break;
+            const long long total = cnt * (long long)per;
+            phase_kernel<<<(int)std::min<long long>((total + 255) / 256, (long long)h->num_sms * 32), 256, 0, h->stream>>>(
+                tmp, alpha + b0, gamma + b0, cnt, pl.dev.twoj, reinterpret_cast<double2 *>(out) + (size_t)b0 * per);
+            h->launches++;
+        }
+        cudaFreeAsync(tmp, h->stream);
+        if (rc) return rc;
+        CU(cudaGetLastError());
+        return WD_OK;
+    }
     const size_t psm = 2 * (size_t)pl.dev.Kp * sizeof(double);
     const int Q = pl.dev.Q;
     const int gy = std::max(1, std::min(64, (Q * Q + 255) / 256));
@@ -1278,11 +1325,14 @@ int wd_d_multi(wd_handle_t h, const int32_t *twoj_list, int32_t nj, const double
     if (rc) return rc;
     CU(cudaSetDevice(h->device));
     if (mem == WD_MEM_DEVICE) {
-        for (int k = 0; k < nj; ++k) {
+        // one symmetry check of the grid for the whole list, at the tolerance of the largest j
+        int tjmax = 0;
+        for (int k = 0; k < nj; ++k) tjmax = std::max(tjmax, twoj_list[k]);
+        if (h->pairing && nb >= 32) h->shared_pair_flag = pair_flag_for(h, beta, nb, tjmax);
+        for (int k = 0; k < nj && rc == WD_OK; ++k)
             rc = contract_device(h, h->plans[twoj_list[k]], nullptr, beta, nullptr, nb, out + offsets[k], false, false);
-            if (rc) return rc;
-        }
-        return WD_OK;
+        h->shared_pair_flag = nullptr;
+        return rc;
     }
     for (int k = 0; k < nj; ++k) {
         rc = contract_host(h, h->plans[twoj_list[k]], nullptr, beta, nullptr, nb, out + offsets[k], false, false);

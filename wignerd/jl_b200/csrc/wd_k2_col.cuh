@@ -96,6 +96,8 @@ __global__ void __launch_bounds__(1024) k2c_pair_check_kernel(const double *__re
     __syncthreads();
     int mine = 0;
     const long long H = nb / 2;
+    // (four independent pairs per thread and pass: the loop is a chain of global-load latencies, 30 us for 10^5 angles unrolled once)
+#pragma unroll 4
     for (long long b = threadIdx.x; b < H; b += blockDim.x) {
         const double d = (beta[b] + beta[nb - 1 - b]) - 3.141592653589793;
         if (!(fabs(d) <= tol)) mine = 1;
