@@ -1,7 +1,7 @@
-# kernel experiments: several builds of the library (WIGNERD_B200_LIB) x env knobs, cfg-2 timing for paired (variant 0) and unpaired (variant 5)
+# kernel experiments: several builds of the library (WIGNERD_B200_LIB) x env knobs, cfg-2 timing for paired (variant 4) and unpaired (variant 5)
 run() { # lib variant extra-env...
   lib=$1; v=$2; shift 2
-  env WIGNERD_B200_LIB=$PWD/wignerd/jl_b200/$lib "$@" timeout 120 python bench.py --config cfg2 --steps 10 --warmup 3 --variant $v --no-cpu-baseline --e2e-angles 1024 > gpurun_out/tmp_b.log 2>&1
+  env WIGNERD_B200_LIB=$PWD/wignerd/jl_b200/$lib "$@" timeout 120 python bench.py --config cfg2 --steps 10 --warmup 3 --variant $v --no-cpu-baseline --no-extras > gpurun_out/tmp_b.log 2>&1
   python - "$lib" "$v" "$*" <<'PY'
 import json,sys
 try:
@@ -11,6 +11,6 @@ except Exception as e:
 PY
 }
 for L in $LIBS; do
-  WIGNERD_B200_LIB=$PWD/wignerd/jl_b200/$L timeout 120 python tools/quick_check.py > gpurun_out/qc_$L.log 2>&1; echo "quick_check $L rc=$?"
-  run $L 0; run $L 5; run $L 0 WD_K2_NOSTORE=1; run $L 5 WD_K2_NOSTORE=1
+  run $L 4; run $L 5; run $L 4 WD_K2_NOSTORE=1; run $L 5 WD_K2_NOSTORE=1
 done
+for L in $LIBS; do run $L 4; run $L 2; done

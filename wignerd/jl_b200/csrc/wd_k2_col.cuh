@@ -178,8 +178,11 @@ __device__ __forceinline__ void k2c_splice_issue(K2CWarp &ws, double *slot, cons
     fence_async_smem();
     __syncwarp();
     // lane -> angle.  (The compiler serialises the 8 copies -- UBLKCP takes uniform registers: ~11 instructions per copy;
-    // tried and dropped: one lane issuing all copies with shuffled parameters 7.4 ms, plain 16-byte vector stores of the
-    // staged windows instead of the TMA 17.9 ms, against 6.5 ms at cfg-2.)
+    // tried and dropped, against 6.4-6.5 ms at cfg-2: one lane issuing all copies with shuffled parameters 7.4 ms; plain
+    // 16-byte vector stores of the staged windows instead of the TMA 17.9 ms; a helper warp per compute warp (208 / 48
+    // registers, full/empty mbarriers per slot) that splices the carries and issues the copies so that the compute warp only
+    // writes its values: 7.5 ms, and 6.2 instead of 4.9 ms with the stores switched off -- eight more warps waiting on
+    // mbarriers cost the DMMA warps more issue slots than the issue loop they took over.)
     if (lane < nv && !ws.nostore) {
         const unsigned long long es = k2c_e0(ws, back, col, lane) + off0;
         const int ph = (int)(es & 3ull), pe = ph + len;
