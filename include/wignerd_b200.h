@@ -152,7 +152,8 @@ int wd_Djmn_batch(wd_handle_t h, const int32_t *twoj, const int32_t *twom, const
  * symmetric about pi/2 take the column-staged kernel with beta <-> pi - beta pairing, other grids k2_real_kernel --
  * decided on the device), 1 = force the plain FP64-ALU kernel, 2 = force the resident DMMA kernels k2_real_kernel /
  * k2_cplx_kernel, 3 = force the streaming DMMA kernel (real d), 4 = force the column-staged DMMA kernel for every grid
- * (paired when symmetric; fails if the table of j does not fit), 5 = the column-staged kernel without pairing. */
+ * (paired when symmetric; fails if the table of j does not fit), 5 = the column-staged kernel without pairing,
+ * 6 = auto with the pairing switched off (every grid is treated as generic). */
 int wd_set_variant(wd_handle_t h, int variant);
 /* host path (mem = WD_MEM_HOST): bytes of output per kernel launch / device-to-host copy (default 512 MiB;
  * two such slabs are double-buffered on the device). */

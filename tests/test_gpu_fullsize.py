@@ -419,3 +419,49 @@ def test_rotate_sh_multi_handle_and_errors(engine):
     with pytest.raises(AssertionError):
         engine.rotate_sh(-1, alm, a, b, g)
     assert engine.rotate_sh(3, np.zeros(16, complex), np.zeros(0), np.zeros(0), np.zeros(0)).shape == (0, 16)
+
+
+@pytest.mark.parametrize("twoj,nb", [(241, 40), (300, 45), (600, 33), (1024, 34), (401, 64)])
+def test_pairing_in_the_streaming_kernel(engine, twoj, nb):
+    """2j > 223: the mu-streaming kernel contracts only the first half of a symmetric grid, its store warps write the mirror matrices"""
+    betas = np.linspace(0, pi, nb)
+    got = engine.wignerd_batch(F(twoj, 2), betas)
+    pick = np.array([0, 1, nb // 2 - 1, nb // 2, (nb + 1) // 2, nb - 2, nb - 1])
+    assert np.abs(got[pick] - cref.wignerd_batch(twoj, betas[pick])).max() < TOL
+    try:
+        engine.set_variant(6)                       # the same kernel without pairing: every matrix
+        unp = engine.wignerd_batch(F(twoj, 2), betas)
+    finally:
+        engine.set_variant(0)
+    assert np.abs(got - unp).max() < 6e-13          # j * tol <= 5e-13 bounds the pairing error (pair_tol in wd_api.cu)
+    assert np.array_equal(got[: (nb + 1) // 2], unp[: (nb + 1) // 2])      # the first half is computed exactly as before
+
+
+@pytest.mark.parametrize("twoj,nb", [(241, 21), (300, 16), (401, 9)])
+def test_complex_D_beyond_the_resident_kernel(engine, twoj, nb):
+    """2j > 223: real d through the streaming DMMA kernel, then the phase pass with the reference's exact cis(-(m alpha + n gamma))"""
+    rng = np.random.default_rng(twoj)
+    a, g, b = rng.uniform(0, 2 * pi, nb), rng.uniform(0, 2 * pi, nb), rng.uniform(0, pi, nb)
+    got = engine.wignerD_batch(F(twoj, 2), a, b, g)
+    assert np.abs(got - cref.wignerD_batch(twoj, a, b, g)).max() < TOL
+    try:
+        engine.set_variant(1)                       # FP64-ALU kernel: independent implementation
+        ref = engine.wignerD_batch(F(twoj, 2), a, b, g)
+    finally:
+        engine.set_variant(0)
+    assert np.abs(got - ref).max() < 1e-12
+
+
+def test_engines_on_two_devices_in_one_thread():
+    """kernel attributes (opt-in shared memory) are per device: a second engine on another GPU must set them again"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    e0, e1 = w.Engine(0), w.Engine(1)
+    try:
+        betas = np.linspace(0, pi, 300)
+        for eng in (e0, e1, e0):
+            assert np.abs(eng.wignerd_batch(100, betas)[[0, 150, 299]] - o.wignerd_batch(100, betas[[0, 150, 299]])).max() < TOL
+            assert np.abs(eng.wignerd_batch(150, betas[:20]) - cref.wignerd_batch(300, betas[:20])).max() < TOL
+    finally:
+        e0.close(); e1.close()

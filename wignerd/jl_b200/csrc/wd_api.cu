@@ -143,6 +143,7 @@ struct wd_handle_s {
     // mapping (0.45 -> 0.27 ms per call at j = 150 on 512 angles).  nullptr: creation failed, the default pool is used.
     cudaMemPool_t pool = nullptr;
     bool attr_set_real[2] = {false, false};
+    bool attr_set_col[2][8] = {};
     int *d_pair = nullptr;            // ring of device flags written by k2c_pair_check_kernel (one per call in flight)
     unsigned pair_idx = 0;
     const int *shared_pair_flag = nullptr;   // wd_d_multi: ONE symmetry check of the angle grid (at the tightest tolerance) for all j
@@ -365,15 +366,15 @@ bool col_fits(wd_handle_t h, const PlanDev &p, size_t *bytes)
 }
 
 template <bool HALF, int GC>
-cudaError_t launch_col_gc(const K2CArgs &c, int grid, size_t smem, size_t optin, cudaStream_t st)
+cudaError_t launch_col_gc(wd_handle_t h, const K2CArgs &c, int grid, size_t smem)
 {
-    static thread_local bool attr_set = false;            // per instantiation; setting it again is harmless
+    bool &attr_set = h->attr_set_col[HALF][GC];           // per handle = per device: the attribute belongs to the device's context
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k2_col_kernel<HALF, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin);
+        cudaError_t e = cudaFuncSetAttribute(k2_col_kernel<HALF, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    k2_col_kernel<HALF, GC><<<grid, K2C_THREADS, smem, st>>>(c);
+    k2_col_kernel<HALF, GC><<<grid, K2C_THREADS, smem, h->stream>>>(c);
     return cudaGetLastError();
 }
 
@@ -408,25 +409,23 @@ int launch_col(wd_handle_t h, const K2Args &a, size_t smem, int mode, const int 
     if (nch < G) items = nch * std::max<long long>(1, std::min<long long>(16, G / nch));
     const int grid = (int)std::min<long long>(items, G);
     const int gc = (a.p.Q + 15) >> 4;
-    const size_t optin = h->smem_optin;
-    cudaStream_t st = h->stream;
     cudaError_t e = cudaErrorInvalidValue;
     if (a.p.twoj & 1) {
         switch (gc) {
-        case 1: e = launch_col_gc<true, 1>(c, grid, smem, optin, st); break;
-        case 2: e = launch_col_gc<true, 2>(c, grid, smem, optin, st); break;
-        case 3: e = launch_col_gc<true, 3>(c, grid, smem, optin, st); break;
-        case 4: e = launch_col_gc<true, 4>(c, grid, smem, optin, st); break;
+        case 1: e = launch_col_gc<true, 1>(h, c, grid, smem); break;
+        case 2: e = launch_col_gc<true, 2>(h, c, grid, smem); break;
+        case 3: e = launch_col_gc<true, 3>(h, c, grid, smem); break;
+        case 4: e = launch_col_gc<true, 4>(h, c, grid, smem); break;
         }
     } else {
         switch (gc) {
-        case 1: e = launch_col_gc<false, 1>(c, grid, smem, optin, st); break;
-        case 2: e = launch_col_gc<false, 2>(c, grid, smem, optin, st); break;
-        case 3: e = launch_col_gc<false, 3>(c, grid, smem, optin, st); break;
-        case 4: e = launch_col_gc<false, 4>(c, grid, smem, optin, st); break;
-        case 5: e = launch_col_gc<false, 5>(c, grid, smem, optin, st); break;
-        case 6: e = launch_col_gc<false, 6>(c, grid, smem, optin, st); break;
-        case 7: e = launch_col_gc<false, 7>(c, grid, smem, optin, st); break;
+        case 1: e = launch_col_gc<false, 1>(h, c, grid, smem); break;
+        case 2: e = launch_col_gc<false, 2>(h, c, grid, smem); break;
+        case 3: e = launch_col_gc<false, 3>(h, c, grid, smem); break;
+        case 4: e = launch_col_gc<false, 4>(h, c, grid, smem); break;
+        case 5: e = launch_col_gc<false, 5>(h, c, grid, smem); break;
+        case 6: e = launch_col_gc<false, 6>(h, c, grid, smem); break;
+        case 7: e = launch_col_gc<false, 7>(h, c, grid, smem); break;
         }
     }
     h->launches++;
@@ -1166,10 +1165,11 @@ int wd_cache_clear(wd_handle_t h)
 int wd_set_variant(wd_handle_t h, int variant)
 {
     if (!h) return fail(WD_ERR_ASSERT, "null handle");
-    if (variant < 0 || variant > 5) return fail(WD_ERR_ASSERT, "variant must be 0..5");
+    if (variant < 0 || variant > 6) return fail(WD_ERR_ASSERT, "variant must be 0..6");
     if (!h->children.empty()) return for_each_child(h, [variant](wd_handle_t c, int) { return wd_set_variant(c, variant); });
     std::lock_guard<std::mutex> lk(h->mtx);
-    h->variant = variant;
+    h->pairing = variant != 6;                            // 6 = auto without the beta <-> pi - beta pairing of symmetric grids
+    h->variant = variant == 6 ? 0 : variant;
     return WD_OK;
 }
 
