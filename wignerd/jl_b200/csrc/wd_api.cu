@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <emmintrin.h>
 #include <condition_variable>
 #include <functional>
 #include <map>
@@ -62,6 +63,22 @@ void shard_bounds(long long n, int rank, int world, int align, long long *lo, lo
     *hi = std::min(hi_c * align, n);
 }
 
+// host copy with non-temporal stores: the destination (a pageable output array, written once) is not read for ownership and
+// does not evict the bounce buffer from the caches
+void stream_copy(char *dst, const char *src, size_t n)
+{
+    if ((((uintptr_t)dst | (uintptr_t)src) & 15) != 0) { memcpy(dst, src, n); return; }
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        const __m128i a = _mm_load_si128((const __m128i *)(src + i)), b = _mm_load_si128((const __m128i *)(src + i + 16));
+        const __m128i c = _mm_load_si128((const __m128i *)(src + i + 32)), d = _mm_load_si128((const __m128i *)(src + i + 48));
+        _mm_stream_si128((__m128i *)(dst + i), a); _mm_stream_si128((__m128i *)(dst + i + 16), b);
+        _mm_stream_si128((__m128i *)(dst + i + 32), c); _mm_stream_si128((__m128i *)(dst + i + 48), d);
+    }
+    _mm_sfence();
+    if (i < n) memcpy(dst + i, src + i, n - i);
+}
+
 // A few persistent host threads that copy one block of memory in parallel (pinned bounce buffer -> pageable destination).
 class CopyPool {
 public:
@@ -96,7 +113,7 @@ private:
             lk.unlock();
             const size_t per = ((b / n_) + 4095) & ~(size_t)4095;
             const size_t lo = std::min(b, per * i), hi = std::min(b, per * (i + 1));
-            if (hi > lo) memcpy(d + lo, s + lo, hi - lo);
+            if (hi > lo) stream_copy(d + lo, s + lo, hi - lo);
             lk.lock();
             if (--left_ == 0) done_.notify_one();
         }
@@ -129,7 +146,7 @@ struct wd_handle_s {
     size_t smem_optin = 0;
     int64_t launches = 0;
     int variant = 0;
-    int pairing = 1;                 // beta <-> pi - beta pairing in k2_col_kernel (wd_set_variant 5 switches it off)
+    int pairing = 1;                 // beta <-> pi - beta pairing in k2_col_kernel (wd_set_variant 6 switches it off)
     size_t slab_bytes = (size_t)512 << 20;   // host path: output slab per kernel launch / device-to-host copy (wd_set_slab_bytes)
     PlanDev *d_table = nullptr;      // plan table indexed by twoj, for K4
     int table_max = -1;
@@ -638,7 +655,7 @@ int ensure_bounce(wd_handle_t h)
         cudaEventCreateWithFlags(&h->ev_bounce[i], cudaEventDisableTiming);
     }
     const unsigned hw = std::thread::hardware_concurrency();
-    h->pool_copy = new CopyPool((int)std::max(2u, std::min(8u, hw / 2)));
+    h->pool_copy = new CopyPool((int)std::max(2u, std::min(12u, hw > 4 ? hw - 4 : hw / 2)));
     return WD_OK;
 }
 
