@@ -5,7 +5,7 @@ import subprocess
 import sys
 
 lib = sys.argv[1]
-want = ["k2_col_kernelILb0ELi7", "k2_real_kernelILb0", "k2_cplx_kernelILb1", "k2_stream_kernelILb0", "k5_gemm_kernelILb1", "k4_jmn_kernelILb0", "k1_eig_kernel"]
+want = ["k2_col_kernelILb0ELi7", "k2_real_kernelILb0", "k2_cplx_kernelILb1", "k2_stream_kernelILb0", "k5_gemm_kernelILb1ELi128", "k4_jmn_kernelILb0", "k1_eig_kernel"]
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 funcs = re.split(r"\n\s*Function : ", txt)[1:]
 for f in funcs:

@@ -785,11 +785,15 @@ int rotate_device(wd_handle_t h, int lmax, const double *alm, long long alm_stri
             reinterpret_cast<const double2 *>(alm), alm_stride, l, alpha, nb, reinterpret_cast<double2 *>(cbuf));
         K5Args g;
         g.U = pl.ufull; g.ld = N; g.N = N; g.l = l; g.nb = nb; g.out_stride = L2;
-        dim3 grid((unsigned)((2 * nb + K5_TN - 1) / K5_TN), (unsigned)((N + K5_TM - 1) / K5_TM));
+        // 64-column tiles when 128-column tiles would leave SMs without a CTA (two CTAs fit per SM)
+        const unsigned rt = (unsigned)((N + K5_TM - 1) / K5_TM);
+        const bool narrow = (long long)rt * ((2 * nb + 127) / 128) < 2LL * h->num_sms;
+        const int TN = narrow ? 64 : 128;
+        dim3 grid((unsigned)((2 * nb + TN - 1) / TN), rt);
         g.in = cbuf; g.out = zbuf; g.angle = beta;
-        k5_gemm_kernel<true><<<grid, 256, 0, h->stream>>>(g);
+        if (narrow) k5_gemm_kernel<true, 64><<<grid, 128, 0, h->stream>>>(g); else k5_gemm_kernel<true, 128><<<grid, 256, 0, h->stream>>>(g);
         g.in = zbuf; g.out = out; g.angle = gamma;
-        k5_gemm_kernel<false><<<grid, 256, 0, h->stream>>>(g);
+        if (narrow) k5_gemm_kernel<false, 64><<<grid, 128, 0, h->stream>>>(g); else k5_gemm_kernel<false, 128><<<grid, 256, 0, h->stream>>>(g);
         h->launches += 3;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) rc = fail(WD_ERR_CUDA, "rotation kernels of l = %d failed to launch: %s", l, cudaGetErrorString(e));

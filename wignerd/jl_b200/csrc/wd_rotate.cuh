@@ -10,7 +10,7 @@
 // 5.9e12 instead of 1.4e14 flops, and 17 GB of coefficients instead of 5.9 TB of matrices).
 //
 // k5_gemm_kernel: FP64 tensor-core GEMM (mma.sync m8n8k4 -> DMMA.8x8x4), CTA tile 64 rows x 128 real columns (= 64
-// complex right-hand sides), 8 warps of 32 x 32, k chunks of 16 staged through shared memory with register prefetch of
+// complex right-hand sides; 64 columns when the batch is small), warps of 32 x 32, k chunks of 16 staged through shared memory with register prefetch of
 // the next chunk; the phase factor of the epilogue is applied to the accumulators (a lane's two adjacent columns are
 // the real and imaginary part of one coefficient).
 #pragma once
@@ -53,9 +53,8 @@ __global__ void __launch_bounds__(256) k5_prephase_kernel(const double2 *__restr
     }
 }
 
-constexpr int K5_TM = 64, K5_TN = 128, K5_TK = 16;
+constexpr int K5_TM = 64, K5_TN = 128, K5_TK = 16;     // CTA tile: 64 rows x TN real columns (TN = 128, or 64 for small batches), k chunks of 16
 constexpr int K5_LDA = K5_TK + 4;            // == 4 (mod 16): conflict-free A fragments
-constexpr int K5_LDB = K5_TN + 4;            // == 4 (mod 16): conflict-free B fragments
 
 struct K5Args {
     const double *U;        // N x N column-major, leading dimension ld
@@ -66,29 +65,32 @@ struct K5Args {
     const double *angle;    // beta (TRANS_A) or gamma: epilogue phase e^{-i v(row) angle_b}, v = row - l
 };
 
-// C[row][col] = sum_k A[row][k] in[k][col];  TRANS_A: A[row][k] = U[k + ld * row] (z = u^T c), else A[row][k] = U[row + ld * k]
-template <bool TRANS_A>
-__global__ void __launch_bounds__(256, 2) k5_gemm_kernel(K5Args a)
+// C[row][col] = sum_k A[row][k] in[k][col];  TRANS_A: A[row][k] = U[k + ld * row] (z = u^T c), else A[row][k] = U[row + ld * k].
+// TN real columns per CTA (2 * TN threads: 2 x TN/32 warps of 32 x 32): 128, or 64 when the batch is too small to fill the GPU.
+template <bool TRANS_A, int TN>
+__global__ void __launch_bounds__(2 * TN, TN == 64 ? 4 : 2) k5_gemm_kernel(K5Args a)
 {
+    constexpr int NT = 2 * TN, LDB = TN + 4;                         // LDB == 4 (mod 16): conflict-free B fragments
     __shared__ __align__(16) double sA[K5_TM * K5_LDA];
-    __shared__ __align__(16) double sB[K5_TK * K5_LDB];
+    __shared__ __align__(16) double sB[K5_TK * LDB];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = lane >> 2, c = lane & 3;
     const int N = a.N;
     const long long C = 2 * a.nb;
     const int row0 = blockIdx.y * K5_TM;
-    const long long col0 = (long long)blockIdx.x * K5_TN;
-    const int wr = (warp >> 2) * 32, wc = (warp & 3) * 32;           // warp tile origin inside the CTA tile
+    const long long col0 = (long long)blockIdx.x * TN;
+    const int wr = (warp / (TN / 32)) * 32, wc = (warp % (TN / 32)) * 32;           // warp tile origin inside the CTA tile
 
     double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 32; ++i) (&acc[0][0][0])[i] = 0.0;
 
-    // global -> register prefetch of one k chunk: A 64 x 16 (4 per thread), B 16 x 128 (8 per thread)
-    double ra[4], rb[8];
+    // global -> register prefetch of one k chunk: A 64 x 16 (1024 / NT per thread), B 16 x TN (8 per thread)
+    constexpr int NA = 1024 / NT;
+    double ra[NA], rb[8];
     auto gload = [&](const int k0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int e = tid + 256 * i;
+        for (int i = 0; i < NA; ++i) {
+            const int e = tid + NT * i;
             int row, k;
             if (TRANS_A) { k = e & 15; row = e >> 4; }                 // k contiguous in memory
             else { row = e & 63; k = e >> 6; }                         // rows contiguous in memory
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(256, 2) k5_gemm_kernel(K5Args a)
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int e = tid + 256 * i, col = e & 127, k = e >> 7;
+            const int e = tid + NT * i, col = e % TN, k = e / TN;
             const int gk = k0 + k;
             const long long gc = col0 + col;
             rb[i] = (gk < N && gc < C) ? a.in[(size_t)gk * C + gc] : 0.0;
@@ -105,16 +107,16 @@ __global__ void __launch_bounds__(256, 2) k5_gemm_kernel(K5Args a)
     };
     auto sstore = [&]() {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int e = tid + 256 * i;
+        for (int i = 0; i < NA; ++i) {
+            const int e = tid + NT * i;
             int row, k;
             if (TRANS_A) { k = e & 15; row = e >> 4; } else { row = e & 63; k = e >> 6; }
             sA[row * K5_LDA + k] = ra[i];
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int e = tid + 256 * i, col = e & 127, k = e >> 7;
-            sB[k * K5_LDB + col] = rb[i];
+            const int e = tid + NT * i, col = e % TN, k = e / TN;
+            sB[k * LDB + col] = rb[i];
         }
     };
     gload(0);
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(256, 2) k5_gemm_kernel(K5Args a)
 #pragma unroll
             for (int i = 0; i < 4; ++i) fa[i] = sA[(wr + 8 * i + r) * K5_LDA + ks + c];
 #pragma unroll
-            for (int jn = 0; jn < 4; ++jn) fb[jn] = sB[(ks + c) * K5_LDB + wc + 8 * jn + r];
+            for (int jn = 0; jn < 4; ++jn) fb[jn] = sB[(ks + c) * LDB + wc + 8 * jn + r];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
