@@ -238,7 +238,7 @@ __device__ __forceinline__ void k2_emit_cplx(const K2Args &a, const K2Ctx &cx, c
     const int ip = i0 + qn, ipr = N - 1 - ip;
     const int col_a = isD ? ipr : ip, col_d = isD ? ip : ipr;       // S: (i,i') up, (ir,i'r) down;  D: (i,i'r) up, (ir,i') down
     const bool both = qn >= cx.zskip;                               // n = 0 mirrors onto itself
-    const bool on_a = !isD || both, on_d0 = isD || both;
+    const bool on_a = (!isD || both) && !a.nostore, on_d0 = (isD || both) && !a.nostore;     // (nostore: experiment knob)
     const int row_a = i0 + qbase, row_d = N - 1 - i0 - qbase;
     const int s_hi = min(16 * gcnt, Q - qbase), s_lo_d = max(0, cx.zskip - qbase);
     const int dib_a = row_a - col_a, dib_d = row_d - col_d;
