@@ -291,18 +291,23 @@ __global__ void __launch_bounds__(K4_THREADS) k4_jmn_kernel(K4Args a)
                 for (int cls = 0; cls < 2; ++cls) {
                     const int kbeg = cls ? K0p : 0, kend = cls ? Kp : K0p;     // (pad columns hold zeros)
                     const int kappa0 = (cls ? (c0 ^ 1) : c0) + 2 * g;          // mu of column kbeg + g: kappa0 (+ 1/2)
-                    double acc = 0.0, sn = 0.0, cs = 1.0;
-                    int it = 0;
+                    double acc = 0.0;
+                    // blocks of 16 steps: exact anchor, then rotations; the loads of 4 steps are in flight together
 #pragma unroll 1
-                    for (int kp = kbeg + g; kp < kend; kp += K4_G, ++it) {
-                        const int kappa = kappa0 + 2 * K4_G * it;
-                        if ((it & 15) == 0) sincos(0.5 * (double)(2 * kappa + par) * beta, &sn, &cs);   // exact anchor, like :199
-                        const double gg = um[kp] * un[kp];
-                        const double w = (kappa | par) ? 2.0 : 1.0;             // mu = 0 has weight 1
-                        acc = fma(w * (odd ? sn : cs), gg, acc);
-                        const double cn = cs * c2 - sn * s2;
-                        sn = fma(sn, c2, cs * s2);
-                        cs = cn;
+                    for (int kp0 = kbeg + g, it0 = 0; kp0 < kend; kp0 += 16 * K4_G, it0 += 16) {
+                        double sn, cs;
+                        sincos(0.5 * (double)(2 * (kappa0 + 2 * K4_G * it0) + par) * beta, &sn, &cs);      // exact anchor, like :199
+                        const int nst = min(16, (kend - kp0 + K4_G - 1) / K4_G);
+#pragma unroll 4
+                        for (int i = 0; i < nst; ++i) {
+                            const int kp = kp0 + i * K4_G;
+                            const double gg = um[kp] * un[kp];
+                            const double w = ((kappa0 + 2 * K4_G * (it0 + i)) | par) ? 2.0 : 1.0;      // mu = 0 has weight 1
+                            acc = fma(w * (odd ? sn : cs), gg, acc);
+                            const double cn = cs * c2 - sn * s2;
+                            sn = fma(sn, c2, cs * s2);
+                            cs = cn;
+                        }
                     }
                     if (cls) acc1 = acc; else acc0 = acc;
                 }
