@@ -142,6 +142,7 @@ struct wd_handle_s {
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     std::mutex mtx;
     std::map<int, Plan> plans;
+    std::vector<void *> table_blocks;   // device allocations that hold the plans' tables (one per eigensolver launch / loaded record)
     int num_sms = 0;
     size_t smem_optin = 0;
     int64_t launches = 0;
@@ -213,29 +214,36 @@ int prepare_batch(wd_handle_t h, const int *todo, size_t n)
         scratch_total += 2 * (size_t)fresh[t].dev.N * fresh[t].dev.Q;
         maxK = std::max(maxK, fresh[t].dev.Q);
     }
-    double *scratch = nullptr;
+    // ONE device block for the tables of the whole batch (a cudaMalloc per plan made "every 2j <= 1024" cost between 0.16 and
+    // 2.5 s depending on the box), 256-byte aligned sub-blocks: the kernels bring UQ in with bulk-TMA loads
+    size_t tables_total = 0;
+    std::vector<size_t> toff(n);
+    for (size_t t = 0; t < n; ++t) {
+        const PlanDev &d = fresh[t].dev;
+        toff[t] = tables_total;
+        tables_total += ((size_t)d.Q * d.ldu + 2 * (size_t)d.Kp + 31) & ~(size_t)31;
+    }
+    double *scratch = nullptr, *block = nullptr;
     EigJob *d_jobs = nullptr;
     auto cleanup = [&](bool drop_tables) {
         if (scratch) cudaFree(scratch);
         if (d_jobs) cudaFree(d_jobs);
-        if (drop_tables) for (auto &pl : fresh) if (pl.uq) cudaFree(pl.uq);
+        if (drop_tables && block) cudaFree(block);
     };
     cudaError_t e = cudaMalloc(&scratch, scratch_total * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&d_jobs, n * sizeof(EigJob));
-    if (e != cudaSuccess) { cleanup(true); return fail(WD_ERR_NOMEM, "cudaMalloc of the eigensolver workspace (%zu bytes) failed: %s", scratch_total * sizeof(double), cudaGetErrorString(e)); }
+    if (e == cudaSuccess) e = cudaMalloc(&block, tables_total * sizeof(double));
+    if (e != cudaSuccess) { cleanup(true); return fail(WD_ERR_NOMEM, "cudaMalloc of the eigensolver workspace and tables (%zu bytes) failed: %s", (scratch_total + tables_total) * sizeof(double), cudaGetErrorString(e)); }
+    cudaMemsetAsync(block, 0, tables_total * sizeof(double), h->stream);
     size_t off = 0;
     for (size_t t = 0; t < n; ++t) {
         Plan &pl = fresh[t];
         const PlanDev &d = pl.dev;
         const size_t nuq = (size_t)d.Q * d.ldu;
-        double *tables = nullptr;                       // one allocation per plan keeps wd_cache_clear simple
-        e = cudaMalloc(&tables, (nuq + 2 * (size_t)d.Kp) * sizeof(double));
-        if (e != cudaSuccess) { cleanup(true); return fail(WD_ERR_NOMEM, "cudaMalloc of the tables of 2j = %d failed: %s", d.twoj, cudaGetErrorString(e)); }
-        pl.uq = tables;
-        pl.mu = tables + nuq;
+        pl.uq = block + toff[t];
+        pl.mu = pl.uq + nuq;
         pl.w = pl.mu + d.Kp;
         pl.dev.uq = pl.uq; pl.dev.mu = pl.mu; pl.dev.w = pl.w;
-        cudaMemsetAsync(pl.uq, 0, nuq * sizeof(double), h->stream);
         EigJob &jb = jobs[t];
         jb.twoj = d.twoj; jb.N = d.N; jb.K = d.Q; jb.K0p = d.K0p; jb.ldu = d.ldu; jb.Kp = d.Kp;
         jb.uq = pl.uq; jb.mu = pl.mu; jb.w = pl.w;
@@ -253,6 +261,7 @@ int prepare_batch(wd_handle_t h, const int *todo, size_t n)
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) { cleanup(true); return fail(WD_ERR_CUDA, "batched eigensolver failed: %s", cudaGetErrorString(e)); }
     cleanup(false);
+    h->table_blocks.push_back(block);
     for (size_t t = 0; t < n; ++t) h->plans[todo[t]] = fresh[t];
     h->table_dirty = true;
     return WD_OK;
@@ -1011,7 +1020,9 @@ static void destroy_single(wd_handle_t h)
 {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (auto &kv : h->plans) { cudaFree(kv.second.uq); if (kv.second.uqc) cudaFree(kv.second.uqc); if (kv.second.ufull) cudaFree(kv.second.ufull); }
+    for (auto &kv : h->plans) { if (kv.second.uqc) cudaFree(kv.second.uqc); if (kv.second.ufull) cudaFree(kv.second.ufull); }
+    for (void *b : h->table_blocks) cudaFree(b);
+    h->table_blocks.clear();
     if (h->d_table) cudaFree(h->d_table);
     if (h->d_flag) cudaFree(h->d_flag);
     if (h->d_pair) cudaFree(h->d_pair);
@@ -1176,7 +1187,9 @@ int wd_cache_clear(wd_handle_t h)
     std::lock_guard<std::mutex> lk(h->mtx);
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (auto &kv : h->plans) { cudaFree(kv.second.uq); if (kv.second.uqc) cudaFree(kv.second.uqc); if (kv.second.ufull) cudaFree(kv.second.ufull); }
+    for (auto &kv : h->plans) { if (kv.second.uqc) cudaFree(kv.second.uqc); if (kv.second.ufull) cudaFree(kv.second.ufull); }
+    for (void *b : h->table_blocks) cudaFree(b);
+    h->table_blocks.clear();
     h->plans.clear();
     h->table_dirty = true;
     if (h->pool) cudaMemPoolTrimTo(h->pool, 0);
@@ -1530,29 +1543,44 @@ static int tables_load_single(wd_handle_t h, const char *path)
         fclose(f);
         return fail(WD_ERR_ARGUMENT, "%s is not a table file of this library (version 1)", path);
     }
-    std::vector<double> buf;
+    // the records that are not cached yet go to ONE host buffer, one device block, one copy
+    std::vector<double> host;
+    std::vector<TabRecord> recs;
+    std::vector<size_t> offs;
     int rc = WD_OK;
     for (int i = 0; i < hd.count && rc == WD_OK; ++i) {
         TabRecord r;
         if (fread(&r, sizeof r, 1, f) != 1) { rc = fail(WD_ERR_ARGUMENT, "%s is truncated", path); break; }
-        Plan pl;
         if (r.twoj < 0 || r.twoj > kMaxTwoJ) { rc = fail(WD_ERR_ARGUMENT, "%s: bad 2j = %d", path, r.twoj); break; }
-        plan_dims(r.twoj, pl.dev);
-        if (r.Q != pl.dev.Q || r.ldu != pl.dev.ldu || r.Kp != pl.dev.Kp) { rc = fail(WD_ERR_ARGUMENT, "%s: layout of 2j = %d does not match this build", path, r.twoj); break; }
-        const size_t nuq = (size_t)r.Q * r.ldu, n = nuq + 2 * (size_t)r.Kp;
-        buf.resize(n);
-        if (fread(buf.data(), sizeof(double), n, f) != n) { rc = fail(WD_ERR_ARGUMENT, "%s is truncated", path); break; }
-        if (h->plans.count(r.twoj)) continue;                      // already cached: keep it
-        double *tables = nullptr;
-        if (cudaMalloc(&tables, n * sizeof(double)) != cudaSuccess) { rc = fail(WD_ERR_NOMEM, "cudaMalloc of the tables of 2j = %d failed", r.twoj); break; }
-        if (cudaMemcpy(tables, buf.data(), n * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(tables); rc = fail(WD_ERR_CUDA, "upload of the tables of 2j = %d failed", r.twoj); break; }
-        pl.uq = tables; pl.mu = tables + nuq; pl.w = pl.mu + r.Kp;
-        pl.dev.uq = pl.uq; pl.dev.mu = pl.mu; pl.dev.w = pl.w;
-        h->plans[r.twoj] = pl;
-        h->table_dirty = true;
+        PlanDev d{};
+        plan_dims(r.twoj, d);
+        if (r.Q != d.Q || r.ldu != d.ldu || r.Kp != d.Kp) { rc = fail(WD_ERR_ARGUMENT, "%s: layout of 2j = %d does not match this build", path, r.twoj); break; }
+        const size_t n = (size_t)r.Q * r.ldu + 2 * (size_t)r.Kp;
+        if (h->plans.count(r.twoj)) {                                 // already cached: keep it, skip the record
+            if (fseek(f, (long)(n * sizeof(double)), SEEK_CUR) != 0) { rc = fail(WD_ERR_ARGUMENT, "%s is truncated", path); break; }
+            continue;
+        }
+        const size_t off = host.size();
+        host.resize(off + ((n + 31) & ~(size_t)31), 0.0);
+        if (fread(host.data() + off, sizeof(double), n, f) != n) { rc = fail(WD_ERR_ARGUMENT, "%s is truncated", path); break; }
+        recs.push_back(r); offs.push_back(off);
     }
     fclose(f);
-    return rc;
+    if (rc || recs.empty()) return rc;
+    double *block = nullptr;
+    if (cudaMalloc(&block, host.size() * sizeof(double)) != cudaSuccess) return fail(WD_ERR_NOMEM, "cudaMalloc of %zu bytes of tables failed", host.size() * sizeof(double));
+    if (cudaMemcpy(block, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(block); return fail(WD_ERR_CUDA, "upload of the tables failed"); }
+    h->table_blocks.push_back(block);
+    for (size_t i = 0; i < recs.size(); ++i) {
+        Plan pl;
+        plan_dims(recs[i].twoj, pl.dev);
+        const size_t nuq = (size_t)recs[i].Q * recs[i].ldu;
+        pl.uq = block + offs[i]; pl.mu = pl.uq + nuq; pl.w = pl.mu + recs[i].Kp;
+        pl.dev.uq = pl.uq; pl.dev.mu = pl.mu; pl.dev.w = pl.w;
+        h->plans[recs[i].twoj] = pl;
+    }
+    h->table_dirty = true;
+    return WD_OK;
 }
 
 int wd_tables_load(wd_handle_t h, const char *path)
