@@ -222,9 +222,10 @@ __global__ void __launch_bounds__(256) k2_plain_kernel(K2Args a)
 // K4: single elements (wignerdjmn / wignerDjmn).  EIGHT lanes per tuple, four tuples per warp.
 //   * Lane g of a group takes the columns kp = g, g + 8, ... of each eigenvector class of the two L2-resident table rows
 //     u[m, .], u[n, .] (coalesced 64-byte pieces), so that its angle advances by a FIXED step from term to term:
-//     mu -> mu + 16.  The reference takes one sincos per term (src/WignerD.jl:199); here a lane anchors (cos, sin)(mu beta)
-//     with an exact sincos(fl(mu beta)) at its first column of each class (and again every 16 steps) and advances it
-//     with a rotation by 16 beta (4 multiply-adds) in between: the trig values stay within ~4e-15 of the reference's.
+//     mu -> mu + 16.  The reference takes one sincos per term (src/WignerD.jl:199); here a lane takes ONE sincos per tuple
+//     (exp(i beta), or exp(i beta / 2) for half-integer j), builds the anchors of its two classes from powers of it and
+//     advances with a rotation by 16 beta (4 multiply-adds) per term; beyond 16 steps (2j > 500) it re-anchors with an
+//     exact sincos(fl(mu beta)).  The trig values stay within ~5e-15 of the reference's.
 //   * Tried: one warp per tuple with one sin or cos per term (round 1): 6.3-6.5 ms for the 10^7 tuples of cfg-5, i.e.
 //     35 % of the chip's measured FP64 sin() issue rate; one THREAD per tuple with the rows staged through shared memory:
 //     7.2 ms (32 tuples of different j per warp: every warp runs to the longest of them).
@@ -285,18 +286,37 @@ __global__ void __launch_bounds__(K4_THREADS) k4_jmn_kernel(K4Args a)
                 const double *um = uq + (size_t)qm * ldu, *un = uq + (size_t)qn * ldu;
                 const int c0 = (Q - 1) & 1, par = tj & 1;
                 const double beta = (kind == 3) ? 1.5707963267948966 : a.beta[t];
-                double s2, c2;
-                sincos((double)(2 * K4_G) * beta, &s2, &c2);             // mu advances by 2 per column of a class, 16 per lane step
+                // ONE sincos per lane and tuple: z = exp(i hb), hb = beta (integer j) or beta / 2 (half-integer j), and its powers
+                // z^2 .. z^32 by squaring.  Every mu of the first 16 steps of a lane is a small multiple of hb (exponent <= 31), so the
+                // anchors of both classes are products of those powers (<= 9 complex multiplications, ~1e-15), and the rotation
+                // by 16 beta of a lane step is z^16 (z^32).  Later blocks (2j > 500) anchor with an exact sincos(fl(mu beta)) like :199.
+                double pr[6], pi[6];
+                sincos(par ? 0.5 * beta : beta, &pi[0], &pr[0]);
+#pragma unroll
+                for (int b = 1; b < 6; ++b) { pr[b] = pr[b - 1] * pr[b - 1] - pi[b - 1] * pi[b - 1]; pi[b] = 2.0 * pr[b - 1] * pi[b - 1]; }
+                const double c2 = par ? pr[5] : pr[4], s2 = par ? pi[5] : pi[4];      // rotation of one lane step: mu -> mu + 16
 #pragma unroll
                 for (int cls = 0; cls < 2; ++cls) {
                     const int kbeg = cls ? K0p : 0, kend = cls ? Kp : K0p;     // (pad columns hold zeros)
                     const int kappa0 = (cls ? (c0 ^ 1) : c0) + 2 * g;          // mu of column kbeg + g: kappa0 (+ 1/2)
                     double acc = 0.0;
-                    // blocks of 16 steps: exact anchor, then rotations; the loads of 4 steps are in flight together
+                    // blocks of 16 steps: anchor, then rotations; the loads of 4 steps are in flight together
 #pragma unroll 1
                     for (int kp0 = kbeg + g, it0 = 0; kp0 < kend; kp0 += 16 * K4_G, it0 += 16) {
                         double sn, cs;
-                        sincos(0.5 * (double)(2 * (kappa0 + 2 * K4_G * it0) + par) * beta, &sn, &cs);      // exact anchor, like :199
+                        if (it0 == 0) {
+                            const int e = par ? 2 * kappa0 + 1 : kappa0;       // mu = e * hb, e <= 31
+                            cs = 1.0; sn = 0.0;
+#pragma unroll
+                            for (int b = 0; b < 5; ++b) {
+                                const double mr = ((e >> b) & 1) ? pr[b] : 1.0, mi = ((e >> b) & 1) ? pi[b] : 0.0;
+                                const double t = cs * mr - sn * mi;
+                                sn = fma(sn, mr, cs * mi);
+                                cs = t;
+                            }
+                        } else {
+                            sincos(0.5 * (double)(2 * (kappa0 + 2 * K4_G * it0) + par) * beta, &sn, &cs);
+                        }
                         const int nst = min(16, (kend - kp0 + K4_G - 1) / K4_G);
 #pragma unroll 4
                         for (int i = 0; i < nst; ++i) {
