@@ -12,7 +12,7 @@ for tjmax, n in [(400, 20000), (1024, 4000), (33, 5000), (7, 3000)]:
     i = (rng.random(n) * (twoj + 1)).astype(np.int32); k = (rng.random(n) * (twoj + 1)).astype(np.int32)
     twom = 2 * i - twoj; twon = 2 * k - twoj
     beta = rng.uniform(-7, 7, n); beta[:5] = [0, np.pi, np.pi / 2, -np.pi, 2 * np.pi]
-    got = e.wignerdjmn_batch(twoj / 2, twom / 2, twon / 2, beta)
+    got = e.wignerdjmn_batch(twoj, twom, twon, beta)          # the batch API takes 2j, 2m, 2n
     ref = cref.wignerdjmn_batch(twoj, twom, twon, beta)
     err = np.abs(got - ref).max()
     print("jmn 2j<=%d n=%d maxerr %.3e" % (tjmax, n, err), flush=True)
