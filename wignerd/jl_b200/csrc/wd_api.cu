@@ -8,6 +8,7 @@
 #include "wd_k2_dmma.cuh"
 #include "wd_k2_stream.cuh"
 #include "wd_k2_col.cuh"
+#include "wd_k3_tma.cuh"
 #include "wd_rotate.cuh"
 
 #include <algorithm>
@@ -162,6 +163,7 @@ struct wd_handle_s {
     cudaMemPool_t pool = nullptr;
     bool attr_set_real[2] = {false, false};
     bool attr_set_col[2][8] = {};
+    bool attr_set_k3t[2][8] = {};
     int *d_pair = nullptr;            // ring of device flags written by k2c_pair_check_kernel (one per call in flight)
     unsigned pair_idx = 0;
     const int *shared_pair_flag = nullptr;   // wd_d_multi: ONE symmetry check of the angle grid (at the tightest tolerance) for all j
@@ -459,6 +461,92 @@ int launch_col(wd_handle_t h, const K2Args &a, size_t smem, int mode, const int 
     return WD_OK;
 }
 
+// Tensor-store DMMA kernel for complex D (k3_tma_kernel, wd_k3_tma.cuh): the default for complex D when its boxes fit
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// cuTensorMapEncodeTiled through the runtime (the library links the static runtime only, not libcuda)
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            f = nullptr;
+        }
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+
+bool k3t_fits(wd_handle_t h, const PlanDev &p, const double *out, size_t *bytes)
+{
+    const K3TSmem L = k3t_smem_layout(p.Q, p.Kp, p.ldu);
+    *bytes = (size_t)L.total * sizeof(double);
+    return k3t_shape_ok(p.twoj) && *bytes <= h->smem_optin && (((uintptr_t)out) & 15) == 0 && encode_tiled_fn() != nullptr;
+}
+
+template <bool HALF, int GC>
+cudaError_t launch_k3t_gc(wd_handle_t h, const K3TArgs &c, const CUtensorMap &ta, const CUtensorMap &td, int grid, size_t smem)
+{
+    bool &attr_set = h->attr_set_k3t[HALF][GC];
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k3_tma_kernel<HALF, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    k3_tma_kernel<HALF, GC><<<grid, K3T_THREADS, smem, h->stream>>>(c, ta, td);
+    return cudaGetLastError();
+}
+
+int launch_k3t(wd_handle_t h, const K2Args &a, size_t smem)
+{
+    K3TArgs c;
+    c.p = a.p; c.alpha = a.alpha; c.beta = a.beta; c.gamma = a.gamma; c.nb = a.nb;
+    c.flags = a.nostore ? K3T_FLAG_NOSTORE : 0;
+    c.handoff = a.handoff;
+    // the output as a 2-d tensor of doubles: dim0 = the 2 N^2 doubles of one matrix, dim1 = the batch; boxes of 8 angles x half a column
+    const int N = a.p.N, Q = a.p.Q, i0 = N - Q;
+    CUtensorMap tm[2];
+    const cuuint64_t dims[2] = {(cuuint64_t)2 * N * N, (cuuint64_t)a.nb};
+    const cuuint64_t strides[1] = {(cuuint64_t)N * N * 16};
+    const cuuint32_t estr[2] = {1, 1};
+    for (int t = 0; t < 2; ++t) {
+        const cuuint32_t box[2] = {(cuuint32_t)(2 * (t == 0 ? Q : i0)), (cuuint32_t)K3T_ANG};
+        const CUresult r = encode_tiled_fn()(&tm[t], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)a.out, dims, strides, box, estr,
+                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(WD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for 2j = %d, %lld matrices", (int)r, a.p.twoj, a.nb);
+    }
+    const long long nch = (a.nb + K3T_ANG - 1) / K3T_ANG;
+    const long long G = h->num_sms;
+    long long items = nch;
+    if (nch < G) items = nch * std::max<long long>(1, std::min<long long>(16, G / nch));
+    const int grid = (int)std::min<long long>(items, G);
+    const int gc = (Q + 15) >> 4;
+    cudaError_t e = cudaErrorInvalidValue;
+    if (a.p.twoj & 1) {
+        switch (gc) {
+        case 1: e = launch_k3t_gc<true, 1>(h, c, tm[0], tm[1], grid, smem); break;
+        case 2: e = launch_k3t_gc<true, 2>(h, c, tm[0], tm[1], grid, smem); break;
+        case 3: e = launch_k3t_gc<true, 3>(h, c, tm[0], tm[1], grid, smem); break;
+        case 4: e = launch_k3t_gc<true, 4>(h, c, tm[0], tm[1], grid, smem); break;
+        }
+    } else {
+        switch (gc) {
+        case 1: e = launch_k3t_gc<false, 1>(h, c, tm[0], tm[1], grid, smem); break;
+        case 2: e = launch_k3t_gc<false, 2>(h, c, tm[0], tm[1], grid, smem); break;
+        case 3: e = launch_k3t_gc<false, 3>(h, c, tm[0], tm[1], grid, smem); break;
+        case 4: e = launch_k3t_gc<false, 4>(h, c, tm[0], tm[1], grid, smem); break;
+        case 5: e = launch_k3t_gc<false, 5>(h, c, tm[0], tm[1], grid, smem); break;
+        }
+    }
+    h->launches++;
+    CU(e);
+    return WD_OK;
+}
+
 // Streaming DMMA kernel (real d, table too large for shared memory): trig table pass + contraction.
 template <bool HALF>
 int launch_stream(wd_handle_t h, const Plan &cpl, const K2Args &a)
@@ -574,7 +662,8 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
     size_t smem = 0;
     const bool fits = cplx ? cplx_fits(h, pl.dev, &smem) : real_fits(h, pl.dev, &smem);
     // variants 4 / 5 select the real-d column kernel only: complex D and Equator requests are dispatched as in auto mode
-    const int variant = ((cplx || equator) && (h->variant == 4 || h->variant == 5)) ? 0 : h->variant;
+    // variant 7 selects the complex-D tensor-store kernel only: real d is dispatched as in auto mode
+    const int variant = (((cplx || equator) && (h->variant == 4 || h->variant == 5)) || ((!cplx || equator) && h->variant == 7)) ? 0 : h->variant;
     if (variant == 2 && !fits) return fail(WD_ERR_UNSUPPORTED, "2j = %d does not fit the DMMA kernel (%zu B of shared memory)", pl.dev.twoj, smem);
     // Equator() requests (single matrices, exact zeros of :230-237) take the plain kernel
     if (variant == 3 && !cplx && !equator) return (pl.dev.twoj & 1) ? launch_stream<true>(h, pl, a) : launch_stream<false>(h, pl, a);
@@ -597,7 +686,14 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
             return half ? launch_real<true>(h, a, smem) : launch_real<false>(h, a, smem);
         }
     }
-    const bool use_dmma = !equator && ((variant == 2) || (variant == 0 && fits));
+    if (cplx && !equator && (variant == 0 || variant == 7)) {
+        // complex D: the tensor-store kernel (k3_tma_kernel) when its boxes fit in shared memory, else k2_cplx_kernel / streaming
+        size_t tsm = 0;
+        const bool tfits = k3t_fits(h, pl.dev, out, &tsm);
+        if (tfits) return launch_k3t(h, a, tsm);
+        if (variant == 7) return fail(WD_ERR_UNSUPPORTED, "2j = %d (or the alignment of the output) does not fit the tensor-store kernel (%zu B of shared memory)", pl.dev.twoj, tsm);
+    }
+    const bool use_dmma = !equator && ((variant == 2) || ((variant == 0 || variant == 7) && fits));
     if (use_dmma && !cplx) return half ? launch_real<true>(h, a, smem) : launch_real<false>(h, a, smem);
     if (use_dmma) return half ? launch_cplx<true>(h, a, smem) : launch_cplx<false>(h, a, smem);
     // real d for a table that does not fit in shared memory: the streaming DMMA kernel
@@ -1199,7 +1295,7 @@ int wd_cache_clear(wd_handle_t h)
 int wd_set_variant(wd_handle_t h, int variant)
 {
     if (!h) return fail(WD_ERR_ASSERT, "null handle");
-    if (variant < 0 || variant > 6) return fail(WD_ERR_ASSERT, "variant must be 0..6");
+    if (variant < 0 || variant > 7) return fail(WD_ERR_ASSERT, "variant must be 0..7");
     if (!h->children.empty()) return for_each_child(h, [variant](wd_handle_t c, int) { return wd_set_variant(c, variant); });
     std::lock_guard<std::mutex> lk(h->mtx);
     h->pairing = variant != 6;                            // 6 = auto without the beta <-> pi - beta pairing of symmetric grids
@@ -1600,6 +1696,7 @@ int64_t wd_k2_shared_bytes(int32_t twoj, int kernel)
     case 1: return (int64_t)k2_smem_layout(p.Q, p.Kp, p.ldu).total * (int64_t)sizeof(double);
     case 2: return (int64_t)k2s_smem_layout((twoj & 1) != 0).total * (int64_t)sizeof(double);
     case 3: return k2c_shape_ok(twoj) ? (int64_t)k2c_smem_layout(p.Q, p.Kp, p.ldu, p.N).total * (int64_t)sizeof(double) : ((int64_t)1 << 40);
+    case 4: return k3t_shape_ok(twoj) ? (int64_t)k3t_smem_layout(p.Q, p.Kp, p.ldu).total * (int64_t)sizeof(double) : ((int64_t)1 << 40);
     default: return -1;
     }
 }
