@@ -411,7 +411,9 @@ def bench_matrices(ctx, name, cfg, steps, warmup, grid="symmetric", e2e=True, pa
     launches = eng.launch_count() - l0
     clk = sampler.stop() if sampler else None
     if cplx:
-        kernel = "k2_cplx_kernel" if twoj <= 223 else "k2_plain_kernel"
+        variant = getattr(ctx, "variant", 0)
+        kernel = ("k3_tma_kernel" if (5 <= twoj <= 127 and variant in (0, 7)) else
+                  "k2_cplx_kernel" if twoj <= 223 else "k2_stream_kernel + phase_kernel")
     elif twoj > 223:
         kernel = "k2_stream_kernel"
     else:
@@ -788,6 +790,7 @@ def main():
     ctx.barrier, ctx.allmax = barrier, allmax
     ctx.eng = w.Engine(ctx.local)
     ctx.eng.set_variant(args.variant)
+    ctx.variant = args.variant
     ctx.hbm_peak = measured_peaks()
     ctx.fp64 = fp64_peaks(ctx)
     extras = args.config == "cfg2" and not args.no_extras and not args.nb and args.variant == 0

@@ -111,7 +111,8 @@ int wd_tables_load(wd_handle_t h, const char *path);
 /* ---- matrices: replaces wignerd/wignerd! (:266-324) and wignerD/wignerD! (:335-357) -- */
 /* nb generic angles -> nb matrices (see layout above).  beta has nb entries. */
 int wd_d_batch(wd_handle_t h, int32_t twoj, const double *beta, int64_t nb, double *out, int mem);
-/* out has nb * N*N complex128 (2 doubles each). */
+/* out has nb * N*N complex128 (2 doubles each); in device memory it must be 16-byte aligned, as every complex128 array is
+ * (WD_ERR_ASSERT otherwise). */
 int wd_D_batch(wd_handle_t h, int32_t twoj, const double *alpha, const double *beta,
                const double *gamma, int64_t nb, double *out, int mem);
 /* Single matrix into HOST memory with the reference's in-place semantics (wignerd!):
@@ -154,15 +155,15 @@ int wd_Djmn_batch(wd_handle_t h, const int32_t *twoj, const int32_t *twom, const
  * k2_cplx_kernel, 3 = force the streaming DMMA kernel (real d), 4 = force the column-staged DMMA kernel for every grid
  * (paired when symmetric; fails if the table of j does not fit), 5 = the column-staged kernel without pairing,
  * 6 = auto with the pairing switched off (every grid is treated as generic), 7 = force the tensor-store complex-D
- * kernel k3_tma_kernel (complex D in auto mode takes it whenever 2j <= 128 fits and the output is 16-byte aligned;
+ * kernel k3_tma_kernel (complex D in auto mode takes it whenever 5 <= 2j <= 127 and the output is 16-byte aligned;
  * forced, a request outside its range fails with WD_ERR_UNSUPPORTED; real d is dispatched as in auto mode). */
 int wd_set_variant(wd_handle_t h, int variant);
 /* host path (mem = WD_MEM_HOST): bytes of output per kernel launch / device-to-host copy (default 512 MiB;
  * two such slabs are double-buffered on the device). */
 int wd_set_slab_bytes(wd_handle_t h, int64_t bytes);
 /* dynamic shared memory (bytes) that the DMMA kernels need for a given 2j -- kernel 0: round-1 resident real-d
- * kernel, 1: resident complex-D kernel, 2: streaming kernel (independent of j), 3: column-staged real-d kernel, 4:
- * tensor-store complex-D kernel (3, 4: a huge value when the shape of j is outside the kernel's range).  A resident kernel is used when this fits the device's opt-in
+ * kernel, 1: resident complex-D kernel, 2: streaming kernel (independent of j), 3: column-staged real-d kernel, 4 / 5:
+ * tensor-store complex-D kernel with 8 / 12 warps (3-5: a huge value when the shape of j is outside the kernel's range).  A resident kernel is used when this fits the device's opt-in
  * limit (232448 bytes on sm_100a).  Pure host arithmetic, no GPU needed; -1 on bad arguments. */
 int64_t wd_k2_shared_bytes(int32_t twoj, int kernel);
 /* FP64 micro-benchmarks used to calibrate the rooflines (bench.py): returns TFLOP/s of a

@@ -27,9 +27,7 @@
 namespace wd {
 
 constexpr int K3T_ANG = 8;
-constexpr int K3T_WARPS = 8;
-constexpr int K3T_THREADS = K3T_WARPS * 32;
-constexpr int K3T_GMAX_INT = 5;             // integer j: Q <= 80 (shared memory ends the range at 2j = 128 anyway)
+constexpr int K3T_GMAX_INT = 4;             // integer j: Q <= 64 (the pipelined epilogue has pieces for four 16-row groups)
 constexpr int K3T_GMAX_HALF = 4;            // half-integer j (both trig functions accumulated): Q <= 64
 constexpr int K3T_FLAG_NOSTORE = 1;         // experiment bit: no tensor stores
 // Lanes c = 2, 3 of an MMA fragment row keep their rows pairwise swapped (row order 1,0,3,2 instead of 0,1,2,3): the 16-byte
@@ -48,13 +46,14 @@ struct K3TArgs {
     long long nb;
     int handoff;              // see K2Args::handoff
     int flags;
+    int tokens;               // main loops that may run at the same time on one SM sub-partition (1; 2 only with 12 warps)
 };
 
 struct K3TSmem {                // offsets in doubles, identical on host and device
     int uq, mu, w, trig, ph, stg, bars, total;
     int ldt, qp, trig_size, ph_size, slot;
 };
-__host__ __device__ inline K3TSmem k3t_smem_layout(int Q, int Kp, int ldu)
+__host__ __device__ inline K3TSmem k3t_smem_layout(int Q, int Kp, int ldu, int nw)
 {
     K3TSmem s;
     s.ldt = Kp | 4;
@@ -72,7 +71,7 @@ __host__ __device__ inline K3TSmem k3t_smem_layout(int Q, int Kp, int ldu)
     o = (o + 1) & ~1;
     s.ph = o;    o += 2 * s.ph_size;
     o = (o + 15) & ~15;                              // boxes start on 128-byte boundaries
-    s.stg = o;   o += K3T_WARPS * 2 * s.slot;
+    s.stg = o;   o += nw * 2 * s.slot;
     s.bars = o;  o += 8;                             // trig_ready[2], trig_free[2], UQ load
     s.total = o;
     return s;
@@ -177,48 +176,110 @@ __device__ __forceinline__ void k3t_emit(K3TWarp &ws, const double (&v)[GC][4], 
     if (ISD || mirror) k3t_box<GC, true>(ws, A, B, me, ISD ? c0 : c1);
 }
 
+// Main loop of one unit: quadrant column qn x all quadrant rows (GC groups of 16) x 8 angles.  MMA roles as in k2c_mainloop
+// (A[8 angles][4 kp] = T(beta, kp) UQ[qn][kp], B[4 kp][8 rows] = UQ[row][kp], even / odd rows of a group in separate tiles).
+// acc[x][g][eo][frag] -- integer j: x = eigenvector class, the butterfly S = P0 + P1, D = P0 - P1 follows;
+// half-integer j (the mirrored pair needs the other trig function, so both are accumulated): the two classes go into ONE
+// accumulator set per trig function -- x = 0: S (main function, both classes), x = 1: D (other function, the A operand of
+// class 1 negated) -- no butterfly and 32 instead of 64 accumulator doubles: what lets three warps per SM sub-partition fit.
+template <bool HALF, int GC>
+__device__ __forceinline__ void k3t_mainloop(double (&acc)[2][GC][2][2], const K2Ctx &cx, const int qn)
+{
+    const int ldu = cx.ldu, ldt = cx.ldt, r = cx.r, c = cx.c, Q = cx.Q;
+    const int pe = qn & 1;
+    const double *tA = (pe ? cx.sTs : cx.sTc) + r * ldt + c;      // trig for the even-row tiles
+    const double *tB = (pe ? cx.sTc : cx.sTs) + r * ldt + c;      // trig for the odd-row tiles
+    const double *un = cx.sUQ + qn * ldu + c;
+    const double *ub = cx.sUQ + (2 * r) * ldu + c;                // rows 16 g + 2 r (even tile) and + 1 (odd tile)
+    const int gs = 16 * ldu;
+    // only the last group can reach past the last row: its two row indices are clamped (never stored)
+    const double *ube = cx.sUQ + min(16 * (GC - 1) + 2 * r, Q - 1) * ldu + c;
+    const double *ubo = cx.sUQ + min(16 * (GC - 1) + 2 * r + 1, Q - 1) * ldu + c;
+    struct Frag { double un, ta, tb, be[GC], bo[GC]; };
+    auto load = [&](Frag &f, const int k) {
+        f.un = un[k]; f.ta = tA[k]; f.tb = tB[k];
+#pragma unroll
+        for (int g = 0; g < GC - 1; ++g) { f.be[g] = ub[g * gs + k]; f.bo[g] = ub[g * gs + ldu + k]; }
+        f.be[GC - 1] = ube[k]; f.bo[GC - 1] = ubo[k];
+    };
+#pragma unroll
+    for (int cls = 0; cls < 2; ++cls) {
+        const int kbeg = cls ? cx.K0p : 0;
+        const int kend = cls ? cx.Kp : cx.K0p;
+        auto step = [&](Frag &f) {
+            f.ta *= f.un; f.tb *= f.un;                               // A = T(beta, kp) * UQ[qn][kp]
+            if (HALF) {
+                const double xa = cls ? flip(f.ta, 0x80000000u) : f.ta, xb = cls ? flip(f.tb, 0x80000000u) : f.tb;
+#pragma unroll
+                for (int g = 0; g < GC; ++g) {
+                    dmma(acc[0][g][0], f.ta, f.be[g]);
+                    dmma(acc[0][g][1], f.tb, f.bo[g]);
+                    dmma(acc[1][g][0], xb, f.be[g]);
+                    dmma(acc[1][g][1], xa, f.bo[g]);
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < GC; ++g) {
+                    dmma(acc[cls][g][0], f.ta, f.be[g]);
+                    dmma(acc[cls][g][1], f.tb, f.bo[g]);
+                }
+            }
+        };
+        // two explicit fragment sets (no register moves): while the DMMAs of one k-step issue from one set, the loads of the
+        // next step land in the other.  A load past the last step reads (and discards) in-bounds shared memory.
+        Frag f0, f1;
+        load(f0, kbeg);
+        int k = kbeg;
+        // hand-off: the next warp of the sub-partition's ring is released after cx.krel pairs of k-steps (see k2c_mainloop)
+        const int krel = !cx.bar_other ? -1 : (cls == 0 ? (cx.krel < 100 ? kbeg + 8 * cx.krel : -1)
+                                                           : (cx.krel >= 100 ? kbeg + 8 * (cx.krel - 100) : -1));
+        bool released = false;
+#pragma unroll 1
+        for (; k + 4 < kend; k += 8) {
+            if (k == krel) { named_bar_arrive(cx.bar_other, 64); released = true; }
+            load(f1, k + 4);
+            step(f0);
+            load(f0, k + 8);
+            step(f1);
+        }
+        if (k < kend) step(f0);
+        if (cx.bar_other && !released && ((cls == 0 && cx.krel < 100) || (cls == 1 && cx.krel >= 100))) named_bar_arrive(cx.bar_other, 64);
+    }
+}
+
 template <bool HALF, int GC>
 __device__ __forceinline__ void k3t_unit(const K2Ctx &cx, K3TWarp &ws, const int qn)
 {
-    constexpr int NALT = HALF ? 2 : 1;
-    double acc[2][GC][2][NALT][2];
+    double acc[2][GC][2][2];
 #pragma unroll
-    for (int i = 0; i < 2 * GC * 2 * NALT * 2; ++i) (&acc[0][0][0][0][0])[i] = 0.0;
-    k2c_mainloop<HALF, GC>(acc, cx, qn);
-    // butterfly: S = P0 + P1, D = P0 - P1 (half-integer j: D from the other trig function); [group][jj]: rows 16 g + 4 c + jj, jj = 2 h + eo
+    for (int i = 0; i < 2 * GC * 2 * 2; ++i) (&acc[0][0][0][0])[i] = 0.0;
+    k3t_mainloop<HALF, GC>(acc, cx, qn);
+    // [group][register jj]: row 16 g + 4 c + (jj ^ swb), jj = 2 h + eo (lanes c = 2, 3 keep their row pairs swapped: K3T_SWAP)
     double vS[GC][4], vD[GC][4];
+    const bool sw = K3T_SWAP && (ws.c & 2);
 #pragma unroll
     for (int g = 0; g < GC; ++g)
 #pragma unroll
-        for (int eo = 0; eo < 2; ++eo)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                vS[g][2 * h + eo] = acc[0][g][eo][0][h] + acc[1][g][eo][0][h];
-                vD[g][2 * h + eo] = acc[0][g][eo][NALT - 1][h] - acc[1][g][eo][NALT - 1][h];
-            }
-    if (K3T_SWAP) {
-        const bool sw = ws.c & 2;
-#pragma unroll
-        for (int g = 0; g < GC; ++g)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const double s0 = vS[g][2 * h], s1 = vS[g][2 * h + 1], d0 = vD[g][2 * h], d1 = vD[g][2 * h + 1];
-                vS[g][2 * h] = sw ? s1 : s0; vS[g][2 * h + 1] = sw ? s0 : s1;
-                vD[g][2 * h] = sw ? d1 : d0; vD[g][2 * h + 1] = sw ? d0 : d1;
-            }
-    }
+        for (int h = 0; h < 2; ++h) {
+            const double s0 = HALF ? acc[0][g][0][h] : acc[0][g][0][h] + acc[1][g][0][h];
+            const double s1 = HALF ? acc[0][g][1][h] : acc[0][g][1][h] + acc[1][g][1][h];
+            const double d0 = HALF ? acc[1][g][0][h] : acc[0][g][0][h] - acc[1][g][0][h];
+            const double d1 = HALF ? acc[1][g][1][h] : acc[0][g][1][h] - acc[1][g][1][h];
+            vS[g][2 * h] = sw ? s1 : s0; vS[g][2 * h + 1] = sw ? s0 : s1;
+            vD[g][2 * h] = sw ? d1 : d0; vD[g][2 * h + 1] = sw ? d0 : d1;
+        }
     k3t_emit<GC, false>(ws, vS, qn);
     k3t_emit<GC, true>(ws, vD, qn);
 }
 
-template <bool HALF, int GC>
-__global__ void __launch_bounds__(K3T_THREADS, 1) k3_tma_kernel(const K3TArgs a, const __grid_constant__ CUtensorMap tm_asc,
+template <bool HALF, int GC, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) k3_tma_kernel(const K3TArgs a, const __grid_constant__ CUtensorMap tm_asc,
                                                                  const __grid_constant__ CUtensorMap tm_desc)
 {
     extern __shared__ __align__(128) double sm[];
     const PlanDev &p = a.p;
     const int Q = p.Q, Kp = p.Kp, ldu = p.ldu, N = p.N;
-    const K3TSmem L = k3t_smem_layout(Q, Kp, ldu);
+    const K3TSmem L = k3t_smem_layout(Q, Kp, ldu, NW);
     const int ldt = L.ldt, qp = L.qp;
     double *sUQ = sm + L.uq, *sMu = sm + L.mu, *sW = sm + L.w;
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(sm + L.bars);
@@ -252,12 +313,12 @@ __global__ void __launch_bounds__(K3T_THREADS, 1) k3_tma_kernel(const K3TArgs a,
         const unsigned uq_bytes = (unsigned)(Q * ldu) * 8u;        // a multiple of 16: ldu is even
         if (tid == 0) {
             mbar_init(uq_bar, 1);
-            for (int b = 0; b < 2; ++b) { mbar_init(trig_ready + b, K3T_WARPS); mbar_init(trig_free + b, K3T_WARPS); }
+            for (int b = 0; b < 2; ++b) { mbar_init(trig_ready + b, NW); mbar_init(trig_free + b, NW); }
             mbar_init_fence();
             mbar_expect_tx(uq_bar, uq_bytes);
             bulk_load(sUQ, p.uq, uq_bytes, uq_bar);
         }
-        for (int i = tid; i < Kp; i += K3T_THREADS) { sMu[i] = p.mu[i]; sW[i] = p.w[i]; }
+        for (int i = tid; i < Kp; i += (NW * 32)) { sMu[i] = p.mu[i]; sW[i] = p.w[i]; }
         __syncthreads();
         mbar_wait(uq_bar, 0);
     }
@@ -269,9 +330,11 @@ __global__ void __launch_bounds__(K3T_THREADS, 1) k3_tma_kernel(const K3TArgs a,
     cx.lane = lane; cx.r = lane >> 2; cx.c = lane & 3;
     cx.b0 = 0;
     cx.krel = a.handoff - 1;
+    // the warps w, w + 4, (w + 8) share an SM sub-partition and hence one DMMA pipe: a token goes round (named barriers), a warp
+    // starts a main loop only when it holds it and passes it on at its release point (see k2_cplx_kernel)
     cx.bar_me = a.handoff ? 2 + warp : 0;
-    cx.bar_other = a.handoff ? 2 + (warp ^ 4) : 0;
-    if (a.handoff && (warp & 4)) named_bar_arrive(cx.bar_other, 64);       // warps 0..3 take the first turn
+    cx.bar_other = a.handoff ? 2 + (warp + 4) % NW : 0;
+    if (a.handoff && warp >= NW - 4 * a.tokens) named_bar_arrive(cx.bar_other, 64);   // warps 0..3 take the first turn (two tokens: and 8..11)
 
     K3TWarp ws;
     ws.stg = sm + L.stg + warp * (2 * L.slot);
@@ -292,7 +355,7 @@ __global__ void __launch_bounds__(K3T_THREADS, 1) k3_tma_kernel(const K3TArgs a,
         const K2CItem itn = item_of(blockIdx.x + kn * G);
         double *tc = sm + L.trig + bn * L.trig_size, *ts = tc + K3T_ANG * ldt;
 #pragma unroll 1
-        for (int idx = tid; idx < K3T_ANG * Kp; idx += K3T_THREADS) {
+        for (int idx = tid; idx < K3T_ANG * Kp; idx += (NW * 32)) {
             const int ang = idx / Kp, kp = idx - ang * Kp;
             long long b = itn.f0 + ang; if (b >= a.nb) b = a.nb - 1;
             double sn, cs;
@@ -303,7 +366,7 @@ __global__ void __launch_bounds__(K3T_THREADS, 1) k3_tma_kernel(const K3TArgs a,
         }
         double *ph = sm + L.ph + bn * L.ph_size;
 #pragma unroll 1
-        for (int idx = tid; idx < 2 * K3T_ANG * Q; idx += K3T_THREADS) {
+        for (int idx = tid; idx < 2 * K3T_ANG * Q; idx += (NW * 32)) {
             const int which = idx / (K3T_ANG * Q), rem2 = idx - which * (K3T_ANG * Q);
             const int ang = rem2 / Q, q = rem2 - ang * Q;
             long long b = itn.f0 + ang; if (b >= a.nb) b = a.nb - 1;
@@ -324,14 +387,14 @@ __global__ void __launch_bounds__(K3T_THREADS, 1) k3_tma_kernel(const K3TArgs a,
         cx.sTc = sm + L.trig + b * L.trig_size; cx.sTs = cx.sTc + K3T_ANG * ldt;
         ws.ph = sm + L.ph + b * L.ph_size;
         ws.f0 = (int)it.f0;
-        // the eight warps work on adjacent columns (rotated from item to item so that the uneven shares even out)
-        const int ncols = it.q_end - it.q_begin, wslot = (warp + (int)(k & 7)) & 7;
-        const int iters = (ncols + K3T_WARPS - 1) / K3T_WARPS;        // the two warps of a pair make the same number of turns
+        // the warps work on adjacent columns (rotated from item to item so that the uneven shares even out)
+        const int ncols = it.q_end - it.q_begin, wslot = (warp + (int)(k % NW)) % NW;
+        const int iters = (ncols + NW - 1) / NW;        // the warps of a ring make the same number of turns
         bool pre = k + 1 >= nmine;
 #pragma unroll 1
         for (int u = 0; u < iters; ++u) {
+            const int qn = it.q_begin + u * NW + wslot;
             if (cx.bar_me) named_bar_sync(cx.bar_me, 64);
-            const int qn = it.q_begin + u * K3T_WARPS + wslot;
             if (qn < it.q_end) k3t_unit<HALF, GC>(cx, ws, qn);
             else if (cx.bar_other) named_bar_arrive(cx.bar_other, 64);        // idle turn: pass the token on
             if (!pre) { prefetch(k + 1); pre = true; }
