@@ -162,8 +162,8 @@ int wd_set_variant(wd_handle_t h, int variant);
  * two such slabs are double-buffered on the device). */
 int wd_set_slab_bytes(wd_handle_t h, int64_t bytes);
 /* dynamic shared memory (bytes) that the DMMA kernels need for a given 2j -- kernel 0: round-1 resident real-d
- * kernel, 1: resident complex-D kernel, 2: streaming kernel (independent of j), 3: column-staged real-d kernel, 4 / 5:
- * tensor-store complex-D kernel with 8 / 12 warps (3-5: a huge value when the shape of j is outside the kernel's range).  A resident kernel is used when this fits the device's opt-in
+ * kernel, 1: resident complex-D kernel, 2: streaming kernel (independent of j), 3: column-staged real-d kernel, 4:
+ * tensor-store complex-D kernel (3, 4: a huge value when the shape of j is outside the kernel's range).  A resident kernel is used when this fits the device's opt-in
  * limit (232448 bytes on sm_100a).  Pure host arithmetic, no GPU needed; -1 on bad arguments. */
 int64_t wd_k2_shared_bytes(int32_t twoj, int kernel);
 /* FP64 micro-benchmarks used to calibrate the rooflines (bench.py): returns TFLOP/s of a

@@ -176,9 +176,6 @@ def test_column_kernel_range_and_new_entry_points_reject_nulls():
     # tensor-store complex-D kernel: cfg-3 (j = 49.5) inside, range 5 <= 2j <= 127 without gaps
     fits4 = [t for t in range(0, 400) if 0 < L.wd_k2_shared_bytes(t, 4) <= limit]
     assert fits4 == list(range(5, 128)), (fits4[:3], fits4[-3:])
-    # ... with three warps per SM sub-partition (12 warps) while their staging slots fit: up to 2j = 101, cfg-3 included
-    fits5 = [t for t in range(0, 400) if 0 < L.wd_k2_shared_bytes(t, 5) <= limit]
-    assert fits5 == list(range(5, 102)), (fits5[:3], fits5[-3:])
     assert L.wd_create_multi(0, None, None) == 2
     h = ctypes.c_void_p()
     assert L.wd_create_multi(0, None, ctypes.byref(h)) == 2   # ndev must be >= 1

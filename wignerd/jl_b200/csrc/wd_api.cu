@@ -163,8 +163,7 @@ struct wd_handle_s {
     cudaMemPool_t pool = nullptr;
     bool attr_set_real[2] = {false, false};
     bool attr_set_col[2][8] = {};
-    bool attr_set_k3t[2][8][2] = {};
-    int k3t_nw_max = 8;              // warps per CTA of k3_tma_kernel: 12 when the staging fits, else 8 (experiment builds: WD_K3T_NW)
+    bool attr_set_k3t[2][8] = {};
     int *d_pair = nullptr;            // ring of device flags written by k2c_pair_check_kernel (one per call in flight)
     unsigned pair_idx = 0;
     const int *shared_pair_flag = nullptr;   // wd_d_multi: ONE symmetry check of the angle grid (at the tightest tolerance) for all j
@@ -481,25 +480,17 @@ EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
-// three warps per SM sub-partition when their staging slots fit next to the table (j = 49.5: 227 008 B), else two
-int k3t_warps(wd_handle_t h, const PlanDev &p, size_t *bytes)
-{
-    if (!k3t_shape_ok(p.twoj)) { *bytes = (size_t)1 << 40; return 0; }
-    for (int nw = (h->k3t_nw_max >= 12 ? 12 : 8); nw >= 8; nw -= 4) {
-        *bytes = (size_t)k3t_smem_layout(p.Q, p.Kp, p.ldu, nw).total * sizeof(double);
-        if (*bytes <= h->smem_optin) return nw;
-    }
-    return 0;
-}
+constexpr int kK3TWarps = 8;         // two warps per SM sub-partition (12 = three was tried: 168 registers spill, see wd_k3_tma.cuh)
 bool k3t_fits(wd_handle_t h, const PlanDev &p, const double *out, size_t *bytes)
 {
-    return k3t_warps(h, p, bytes) != 0 && (((uintptr_t)out) & 15) == 0 && encode_tiled_fn() != nullptr;
+    *bytes = (size_t)k3t_smem_layout(p.Q, p.Kp, p.ldu, kK3TWarps).total * sizeof(double);
+    return k3t_shape_ok(p.twoj) && *bytes <= h->smem_optin && (((uintptr_t)out) & 15) == 0 && encode_tiled_fn() != nullptr;
 }
 
 template <bool HALF, int GC, int NW>
 cudaError_t launch_k3t_gc(wd_handle_t h, const K3TArgs &c, const CUtensorMap &ta, const CUtensorMap &td, int grid, size_t smem)
 {
-    bool &attr_set = h->attr_set_k3t[HALF][GC][NW == 12];
+    bool &attr_set = h->attr_set_k3t[HALF][GC];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k3_tma_kernel<HALF, GC, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
         if (e != cudaSuccess) return e;
@@ -509,23 +500,17 @@ cudaError_t launch_k3t_gc(wd_handle_t h, const K3TArgs &c, const CUtensorMap &ta
     return cudaGetLastError();
 }
 template <bool HALF, int GC>
-cudaError_t launch_k3t_nw(wd_handle_t h, const K3TArgs &c, const CUtensorMap &ta, const CUtensorMap &td, int grid, size_t smem, int nw)
+cudaError_t launch_k3t_nw(wd_handle_t h, const K3TArgs &c, const CUtensorMap &ta, const CUtensorMap &td, int grid, size_t smem)
 {
-    return nw == 12 ? launch_k3t_gc<HALF, GC, 12>(h, c, ta, td, grid, smem) : launch_k3t_gc<HALF, GC, 8>(h, c, ta, td, grid, smem);
+    return launch_k3t_gc<HALF, GC, kK3TWarps>(h, c, ta, td, grid, smem);
 }
 
-int launch_k3t(wd_handle_t h, const K2Args &a)
+int launch_k3t(wd_handle_t h, const K2Args &a, size_t smem)
 {
-    size_t smem = 0;
-    const int nw = k3t_warps(h, a.p, &smem);
     K3TArgs c;
     c.p = a.p; c.alpha = a.alpha; c.beta = a.beta; c.gamma = a.gamma; c.nb = a.nb;
     c.flags = a.nostore ? K3T_FLAG_NOSTORE : 0;
     c.handoff = a.handoff;
-    c.tokens = 1;
-#ifdef WD_EXPERIMENT
-    { const char *e = getenv("WD_K3T_TOKENS"); if (e && nw == 12) c.tokens = atoi(e) == 2 ? 2 : 1; }
-#endif
     // the output as a 2-d tensor of doubles: dim0 = the 2 N^2 doubles of one matrix, dim1 = the batch; boxes of 8 angles x half a column
     const int N = a.p.N, Q = a.p.Q, i0 = N - Q;
     CUtensorMap tm[2];
@@ -548,17 +533,17 @@ int launch_k3t(wd_handle_t h, const K2Args &a)
     cudaError_t e = cudaErrorInvalidValue;
     if (a.p.twoj & 1) {
         switch (gc) {
-        case 1: e = launch_k3t_nw<true, 1>(h, c, tm[0], tm[1], grid, smem, nw); break;
-        case 2: e = launch_k3t_nw<true, 2>(h, c, tm[0], tm[1], grid, smem, nw); break;
-        case 3: e = launch_k3t_nw<true, 3>(h, c, tm[0], tm[1], grid, smem, nw); break;
-        case 4: e = launch_k3t_nw<true, 4>(h, c, tm[0], tm[1], grid, smem, nw); break;
+        case 1: e = launch_k3t_nw<true, 1>(h, c, tm[0], tm[1], grid, smem); break;
+        case 2: e = launch_k3t_nw<true, 2>(h, c, tm[0], tm[1], grid, smem); break;
+        case 3: e = launch_k3t_nw<true, 3>(h, c, tm[0], tm[1], grid, smem); break;
+        case 4: e = launch_k3t_nw<true, 4>(h, c, tm[0], tm[1], grid, smem); break;
         }
     } else {
         switch (gc) {
-        case 1: e = launch_k3t_nw<false, 1>(h, c, tm[0], tm[1], grid, smem, nw); break;
-        case 2: e = launch_k3t_nw<false, 2>(h, c, tm[0], tm[1], grid, smem, nw); break;
-        case 3: e = launch_k3t_nw<false, 3>(h, c, tm[0], tm[1], grid, smem, nw); break;
-        case 4: e = launch_k3t_nw<false, 4>(h, c, tm[0], tm[1], grid, smem, nw); break;
+        case 1: e = launch_k3t_nw<false, 1>(h, c, tm[0], tm[1], grid, smem); break;
+        case 2: e = launch_k3t_nw<false, 2>(h, c, tm[0], tm[1], grid, smem); break;
+        case 3: e = launch_k3t_nw<false, 3>(h, c, tm[0], tm[1], grid, smem); break;
+        case 4: e = launch_k3t_nw<false, 4>(h, c, tm[0], tm[1], grid, smem); break;
         }
     }
     h->launches++;
@@ -665,8 +650,6 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
     {
         const char *e = getenv("WD_K2_NOSTORE");         // kernel-experiment knob: 1 = no store instructions (SM-side time)
         if (e) a.nostore = atoi(e) != 0;
-        e = getenv("WD_K3T_NW");                         // 8: never three warps per sub-partition in k3_tma_kernel
-        if (e) h->k3t_nw_max = atoi(e);
     }
 #endif
     {
@@ -713,7 +696,7 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
         // complex D: the tensor-store kernel (k3_tma_kernel) when its boxes fit in shared memory, else k2_cplx_kernel / streaming
         size_t tsm = 0;
         const bool tfits = k3t_fits(h, pl.dev, out, &tsm);
-        if (tfits) return launch_k3t(h, a);
+        if (tfits) return launch_k3t(h, a, tsm);
         if (variant == 7) return fail(WD_ERR_UNSUPPORTED, "2j = %d (or the alignment of the output) does not fit the tensor-store kernel (%zu B of shared memory)", pl.dev.twoj, tsm);
     }
     const bool use_dmma = !equator && ((variant == 2) || ((variant == 0 || variant == 7) && fits));
@@ -1720,8 +1703,7 @@ int64_t wd_k2_shared_bytes(int32_t twoj, int kernel)
     case 1: return (int64_t)k2_smem_layout(p.Q, p.Kp, p.ldu).total * (int64_t)sizeof(double);
     case 2: return (int64_t)k2s_smem_layout((twoj & 1) != 0).total * (int64_t)sizeof(double);
     case 3: return k2c_shape_ok(twoj) ? (int64_t)k2c_smem_layout(p.Q, p.Kp, p.ldu, p.N).total * (int64_t)sizeof(double) : ((int64_t)1 << 40);
-    case 4: return k3t_shape_ok(twoj) ? (int64_t)k3t_smem_layout(p.Q, p.Kp, p.ldu, 8).total * (int64_t)sizeof(double) : ((int64_t)1 << 40);
-    case 5: return k3t_shape_ok(twoj) ? (int64_t)k3t_smem_layout(p.Q, p.Kp, p.ldu, 12).total * (int64_t)sizeof(double) : ((int64_t)1 << 40);
+    case 4: return k3t_shape_ok(twoj) ? (int64_t)k3t_smem_layout(p.Q, p.Kp, p.ldu, kK3TWarps).total * (int64_t)sizeof(double) : ((int64_t)1 << 40);
     default: return -1;
     }
 }

@@ -46,7 +46,6 @@ struct K3TArgs {
     long long nb;
     int handoff;              // see K2Args::handoff
     int flags;
-    int tokens;               // main loops that may run at the same time on one SM sub-partition (1; 2 only with 12 warps)
 };
 
 struct K3TSmem {                // offsets in doubles, identical on host and device
@@ -334,7 +333,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k3_tma_kernel(const K3TArgs a, con
     // starts a main loop only when it holds it and passes it on at its release point (see k2_cplx_kernel)
     cx.bar_me = a.handoff ? 2 + warp : 0;
     cx.bar_other = a.handoff ? 2 + (warp + 4) % NW : 0;
-    if (a.handoff && warp >= NW - 4 * a.tokens) named_bar_arrive(cx.bar_other, 64);   // warps 0..3 take the first turn (two tokens: and 8..11)
+    if (a.handoff && warp >= NW - 4) named_bar_arrive(cx.bar_other, 64);   // warps 0..3 take the first turn
 
     K3TWarp ws;
     ws.stg = sm + L.stg + warp * (2 * L.slot);
