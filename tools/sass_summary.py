@@ -5,7 +5,7 @@ import subprocess
 import sys
 
 lib = sys.argv[1]
-want = ["k2_col_kernelILb0ELi7", "k2_real_kernelILb0", "k2_cplx_kernelILb1", "k2_stream_kernelILb0", "k5_gemm_kernelILb1ELi128", "k4_jmn_kernelILb0", "k1_eig_kernel"]
+want = ["k2_col_kernelILb0ELi7", "k2_real_kernelILb0", "k2_cplx_kernelILb1", "k3_tma_kernelILb1ELi4", "k2_stream_kernelILb0", "k5_gemm_kernelILb1ELi128", "k4_jmn_kernelILb0", "k1_eig_kernel"]
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 funcs = re.split(r"\n\s*Function : ", txt)[1:]
 for f in funcs:
@@ -23,7 +23,7 @@ for f in funcs:
         op = toks[1] if toks[0].startswith("@") else toks[0]
         op = op.split(".")[0] if not op.startswith(("DMMA", "UBLKCP", "SYNCS", "UTMA")) else op
         hist[op] = hist.get(op, 0) + 1
-    key = ["DMMA.8x8x4", "UBLKCP.S.G", "UBLKCP.G.S", "UTMACMDFLUSH", "SYNCS.EXCH.64", "SYNCS.ARRIVE.TRANS64", "SYNCS.ARRIVE.TRANS64.A1T0",
+    key = ["DMMA.8x8x4", "UBLKCP.S.G", "UBLKCP.G.S", "UTMASTG.2D", "UTMACMDFLUSH", "SYNCS.EXCH.64", "SYNCS.ARRIVE.TRANS64", "SYNCS.ARRIVE.TRANS64.A1T0",
            "SYNCS.PHASECHK.TRANS64.TRYWAIT", "BAR", "FENCE", "MEMBAR", "USETMAXREG", "LDS", "STS", "LDG", "STG", "LDL", "STL", "DMUL", "DFMA", "DADD", "SHFL", "R2UR"]
     print(f"== {name}  ({len(ins)} instructions)")
     print("   " + "  ".join(f"{k}:{hist[k]}" for k in key if k in hist))

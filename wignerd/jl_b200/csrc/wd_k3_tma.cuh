@@ -175,95 +175,30 @@ __device__ __forceinline__ void k3t_emit(K3TWarp &ws, const double (&v)[GC][4], 
     if (ISD || mirror) k3t_box<GC, true>(ws, A, B, me, ISD ? c0 : c1);
 }
 
-// Main loop of one unit: quadrant column qn x all quadrant rows (GC groups of 16) x 8 angles.  MMA roles as in k2c_mainloop
-// (A[8 angles][4 kp] = T(beta, kp) UQ[qn][kp], B[4 kp][8 rows] = UQ[row][kp], even / odd rows of a group in separate tiles).
-// acc[x][g][eo][frag] -- integer j: x = eigenvector class, the butterfly S = P0 + P1, D = P0 - P1 follows;
-// half-integer j (the mirrored pair needs the other trig function, so both are accumulated): the two classes go into ONE
-// accumulator set per trig function -- x = 0: S (main function, both classes), x = 1: D (other function, the A operand of
-// class 1 negated) -- no butterfly and 32 instead of 64 accumulator doubles: what lets three warps per SM sub-partition fit.
-template <bool HALF, int GC>
-__device__ __forceinline__ void k3t_mainloop(double (&acc)[2][GC][2][2], const K2Ctx &cx, const int qn)
-{
-    const int ldu = cx.ldu, ldt = cx.ldt, r = cx.r, c = cx.c, Q = cx.Q;
-    const int pe = qn & 1;
-    const double *tA = (pe ? cx.sTs : cx.sTc) + r * ldt + c;      // trig for the even-row tiles
-    const double *tB = (pe ? cx.sTc : cx.sTs) + r * ldt + c;      // trig for the odd-row tiles
-    const double *un = cx.sUQ + qn * ldu + c;
-    const double *ub = cx.sUQ + (2 * r) * ldu + c;                // rows 16 g + 2 r (even tile) and + 1 (odd tile)
-    const int gs = 16 * ldu;
-    // only the last group can reach past the last row: its two row indices are clamped (never stored)
-    const double *ube = cx.sUQ + min(16 * (GC - 1) + 2 * r, Q - 1) * ldu + c;
-    const double *ubo = cx.sUQ + min(16 * (GC - 1) + 2 * r + 1, Q - 1) * ldu + c;
-    struct Frag { double un, ta, tb, be[GC], bo[GC]; };
-    auto load = [&](Frag &f, const int k) {
-        f.un = un[k]; f.ta = tA[k]; f.tb = tB[k];
-#pragma unroll
-        for (int g = 0; g < GC - 1; ++g) { f.be[g] = ub[g * gs + k]; f.bo[g] = ub[g * gs + ldu + k]; }
-        f.be[GC - 1] = ube[k]; f.bo[GC - 1] = ubo[k];
-    };
-#pragma unroll
-    for (int cls = 0; cls < 2; ++cls) {
-        const int kbeg = cls ? cx.K0p : 0;
-        const int kend = cls ? cx.Kp : cx.K0p;
-        auto step = [&](Frag &f) {
-            f.ta *= f.un; f.tb *= f.un;                               // A = T(beta, kp) * UQ[qn][kp]
-            if (HALF) {
-                const double xa = cls ? flip(f.ta, 0x80000000u) : f.ta, xb = cls ? flip(f.tb, 0x80000000u) : f.tb;
-#pragma unroll
-                for (int g = 0; g < GC; ++g) {
-                    dmma(acc[0][g][0], f.ta, f.be[g]);
-                    dmma(acc[0][g][1], f.tb, f.bo[g]);
-                    dmma(acc[1][g][0], xb, f.be[g]);
-                    dmma(acc[1][g][1], xa, f.bo[g]);
-                }
-            } else {
-#pragma unroll
-                for (int g = 0; g < GC; ++g) {
-                    dmma(acc[cls][g][0], f.ta, f.be[g]);
-                    dmma(acc[cls][g][1], f.tb, f.bo[g]);
-                }
-            }
-        };
-        // two explicit fragment sets (no register moves): while the DMMAs of one k-step issue from one set, the loads of the
-        // next step land in the other.  A load past the last step reads (and discards) in-bounds shared memory.
-        Frag f0, f1;
-        load(f0, kbeg);
-        int k = kbeg;
-        // hand-off: the next warp of the sub-partition's ring is released after cx.krel pairs of k-steps (see k2c_mainloop)
-        const int krel = !cx.bar_other ? -1 : (cls == 0 ? (cx.krel < 100 ? kbeg + 8 * cx.krel : -1)
-                                                           : (cx.krel >= 100 ? kbeg + 8 * (cx.krel - 100) : -1));
-        bool released = false;
-#pragma unroll 1
-        for (; k + 4 < kend; k += 8) {
-            if (k == krel) { named_bar_arrive(cx.bar_other, 64); released = true; }
-            load(f1, k + 4);
-            step(f0);
-            load(f0, k + 8);
-            step(f1);
-        }
-        if (k < kend) step(f0);
-        if (cx.bar_other && !released && ((cls == 0 && cx.krel < 100) || (cls == 1 && cx.krel >= 100))) named_bar_arrive(cx.bar_other, 64);
-    }
-}
-
+// One unit: quadrant column qn x all quadrant rows (GC groups of 16) x 8 angles.  The main loop IS k2_col_kernel's
+// (k2c_mainloop): the same DMMAs in the same order as the real-d kernels, so that wignerD(j, 0, beta, 0) equals wignerd(j, beta)
+// bit for bit, which the reference's tests demand (test/runtests.jl:343).  (Tried: for half-integer j, both eigenvector classes
+// accumulated into ONE accumulator set per trig function -- S = main function, D = other function with the A operand of class 1
+// negated -- no butterfly, 32 instead of 64 accumulator doubles: 3.22 instead of 3.25 ms at cfg-3, but the sums round
+// differently from the real-d path and that equality is lost.)
 template <bool HALF, int GC>
 __device__ __forceinline__ void k3t_unit(const K2Ctx &cx, K3TWarp &ws, const int qn)
 {
-    double acc[2][GC][2][2];
+    constexpr int NALT = HALF ? 2 : 1;
+    double acc[2][GC][2][NALT][2];
 #pragma unroll
-    for (int i = 0; i < 2 * GC * 2 * 2; ++i) (&acc[0][0][0][0])[i] = 0.0;
-    k3t_mainloop<HALF, GC>(acc, cx, qn);
-    // [group][register jj]: row 16 g + 4 c + (jj ^ swb), jj = 2 h + eo (lanes c = 2, 3 keep their row pairs swapped: K3T_SWAP)
+    for (int i = 0; i < 2 * GC * 2 * NALT * 2; ++i) (&acc[0][0][0][0][0])[i] = 0.0;
+    k2c_mainloop<HALF, GC>(acc, cx, qn);
+    // butterfly: S = P0 + P1, D = P0 - P1 (half-integer j: D from the other trig function).  [group][register jj]: row
+    // 16 g + 4 c + (jj ^ swb), jj = 2 h + eo (lanes c = 2, 3 keep their row pairs swapped: K3T_SWAP)
     double vS[GC][4], vD[GC][4];
     const bool sw = K3T_SWAP && (ws.c & 2);
 #pragma unroll
     for (int g = 0; g < GC; ++g)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const double s0 = HALF ? acc[0][g][0][h] : acc[0][g][0][h] + acc[1][g][0][h];
-            const double s1 = HALF ? acc[0][g][1][h] : acc[0][g][1][h] + acc[1][g][1][h];
-            const double d0 = HALF ? acc[1][g][0][h] : acc[0][g][0][h] - acc[1][g][0][h];
-            const double d1 = HALF ? acc[1][g][1][h] : acc[0][g][1][h] - acc[1][g][1][h];
+            const double s0 = acc[0][g][0][0][h] + acc[1][g][0][0][h], s1 = acc[0][g][1][0][h] + acc[1][g][1][0][h];
+            const double d0 = acc[0][g][0][NALT - 1][h] - acc[1][g][0][NALT - 1][h], d1 = acc[0][g][1][NALT - 1][h] - acc[1][g][1][NALT - 1][h];
             vS[g][2 * h] = sw ? s1 : s0; vS[g][2 * h + 1] = sw ? s0 : s1;
             vD[g][2 * h] = sw ? d1 : d0; vD[g][2 * h + 1] = sw ? d0 : d1;
         }
