@@ -12,7 +12,8 @@
 //   * the lane that holds an accumulator also holds everything its phase needs: cos/sin(n gamma) of its angle (one pair per
 //     unit) and cos/sin(m alpha) of its 4 consecutive rows (two 16-byte loads per table and 16-row group).  Per row and angle:
 //     4 FP64 operations for (re, im) of the phase, 2 multiplies, and the value goes to its ascending target as (A, B) and to
-//     its mirror target as +-(A, -B) (conjugate up to the sign sigma): 0.25 instructions per output element, all independent.
+//     its mirror target as +-(A, -B) (conjugate up to the sign sigma): 760 independent instructions per unit of 1600 outputs
+//     with no global-memory instruction among them.
 //
 // Boxes of a unit (column n = qn >= 0, c0 = j+n, c1 = j-n; S = P0 + P1, D = P0 - P1; x = ca cg, y = sa sg, z = sa cg, w = ca sg):
 //     c0 rows m >= 0  <- S (x - y, -(z + w))      c1 rows m <= 0  <- S (x - y, +(z + w))     (sign sigma(row - col) each)
@@ -20,6 +21,11 @@
 // Staging: two box slots per warp ([8 angles][half column] complex, dense = the layout the tensor store reads), the store of
 // box t-2 must have read its slot before box t is written (cp.async.bulk.wait_group.read 1).
 // Trig and phase tables of item k+1 are made during item k (mbarriers, no CTA barrier), pair hand-off as in k2_col_kernel.
+//
+// Measured at cfg-3 (one B200): 3.24 ms = 4.93 TB/s = 75 % of the measured HBM write roof (k2_cplx_kernel: 3.96 ms); without
+// its tensor stores 3.14 ms, DMMA pipe 59 % (floor 1.94 ms): the SM side binds.  What was tried around it (a third staging
+// box, 12 warps, software-pipelined epilogue pieces, merged accumulators, release points): DESIGN.md section 4.
+// NW (warps per CTA) is a template parameter because the 12-warp form was measured; the library instantiates NW = 8 only.
 #pragma once
 #include <cuda.h>
 #include "wd_k2_col.cuh"
@@ -27,7 +33,7 @@
 namespace wd {
 
 constexpr int K3T_ANG = 8;
-constexpr int K3T_GMAX_INT = 4;             // integer j: Q <= 64 (the pipelined epilogue has pieces for four 16-row groups)
+constexpr int K3T_GMAX_INT = 4;             // integer j: Q <= 64 (more 16-row groups do not fit in 255 registers without spills)
 constexpr int K3T_GMAX_HALF = 4;            // half-integer j (both trig functions accumulated): Q <= 64
 constexpr int K3T_FLAG_NOSTORE = 1;         // experiment bit: no tensor stores
 // Lanes c = 2, 3 of an MMA fragment row keep their rows pairwise swapped (row order 1,0,3,2 instead of 0,1,2,3): the 16-byte
