@@ -412,8 +412,7 @@ def bench_matrices(ctx, name, cfg, steps, warmup, grid="symmetric", e2e=True, pa
     clk = sampler.stop() if sampler else None
     if cplx:
         variant = getattr(ctx, "variant", 0)
-        kernel = ("k3_tmap_kernel" if (5 <= twoj <= 127 and variant == 8) else
-                  "k3_tma_kernel" if (5 <= twoj <= 127 and variant in (0, 7)) else
+        kernel = ("k3_tma_kernel" if (5 <= twoj <= 127 and variant in (0, 7)) else
                   "k2_cplx_kernel" if twoj <= 223 else "k2_stream_kernel + phase_kernel")
     elif twoj > 223:
         kernel = "k2_stream_kernel"

@@ -128,103 +128,3 @@ def test_k3t_epilogue_model_zero_euler_angles_are_exact():
         assert np.array_equal(got.real[:, i0:, i0:], ref[:, i0:, i0:])
         assert np.abs(got.real - ref).max() < 1e-14
 
-
-# ---- k3_tmap_kernel (wd_k3_tma_p.cuh): units of two 16-row groups, boxes of a quarter column ---------------------------
-def k3p_box(Q, zskip, part):
-    q0 = 32 * part
-    wa = min(32, Q - q0)
-    p0 = max(0, Q - (q0 + 32))
-    wd = (Q - 1 - q0 - (zskip if part == 0 else 0)) - p0 + 1
-    return wa, wd, p0
-
-
-def model_parts(twoj, al, be, ga):
-    N = twoj + 1
-    Q = (N + 1) // 2
-    i0 = N - Q
-    zskip = 0 if twoj & 1 else 1
-    GC = (Q + 15) >> 4
-    upc = (GC + 1) // 2
-    qp = 32 * upc + 2
-    nb = 8
-    dm = o.wignerd_batch(twoj / 2, be)
-    mem = np.full((nb, 2 * N * N), np.nan)
-    mhalf = 0.5 * (twoj & 1)
-    ph = np.full((4, 8, qp), np.nan)
-    for which, angs in ((0, al), (1, ga)):
-        for ang in range(8):
-            for q in range(Q):
-                x = (q + mhalf) * angs[ang]
-                ph[2 * which, ang, perm(q)] = np.cos(x)
-                ph[2 * which + 1, ang, perm(q)] = np.sin(x)
-
-    def sig(i, ip):
-        return -1.0 if ((i - ip) & 3) in (1, 2) else 1.0
-
-    for qn in range(Q):
-        ip = i0 + qn
-        ipr = N - 1 - ip
-        for part in range(upc):
-            g0 = 2 * part
-            q0 = 16 * g0
-            wa, wd, p0 = k3p_box(Q, zskip, part)
-            for isd in (False, True):                                # k3p_emit<ISD>
-                boxes = {False: np.full(8 * 2 * wa, np.nan), True: np.full(8 * 2 * max(wd, 1), np.nan)}
-                for lane in range(32):
-                    r, c = lane >> 2, lane & 3
-                    swb = 1 if (c & 2) else 0
-                    cg, sg0 = ph[2, r, perm(qn)], ph[3, r, perm(qn)]
-                    sgx = sg0 if isd else -sg0
-                    d0 = (qn + 1 - zskip) if isd else -qn
-                    ms = [sigma_bit(d0 + (jj ^ swb)) for jj in range(4)]
-                    me = [(d0 + (jj ^ swb)) & 1 for jj in range(4)]
-                    for g in range(2):
-                        for jj in range(4):
-                            ql = 16 * g + 4 * c + (jj ^ swb)
-                            q = q0 + ql
-                            if q < Q:
-                                i = i0 + q
-                                v = sig(i, ipr) * dm[r, i, ipr] if isd else sig(i, ip) * dm[r, i, ip]
-                            else:
-                                v = np.nan
-                            ca, sa = ph[0, r, q0 + 16 * g + 4 * c + jj], ph[1, r, q0 + 16 * g + 4 * c + jj]
-                            y, z = sa * sgx, sa * cg
-                            re, im = ca * cg + y, ca * sgx - z
-                            vv = flip(v, ms[jj])
-                            A, B = vv * re, vv * im
-                            for desc in (False, True):               # k3p_boxout<DESC>
-                                wbox = wd if desc else wa
-                                pos0 = (Q - 1 - q0) - p0 if desc else 0
-                                ok = q < Q and not (desc and zskip and q == 0)
-                                if ok:
-                                    if desc:
-                                        off, val = r * 2 * wbox + 2 * (pos0 - ql), (flip(A, me[jj]), flip(B, me[jj] ^ 1))
-                                    else:
-                                        off, val = r * 2 * wbox + 2 * (pos0 + ql), (A, B)
-                                    assert r * 2 * wbox <= off and off + 1 < (r + 1) * 2 * wbox     # inside the lane's box row
-                                    assert np.isnan(boxes[desc][off])
-                                    boxes[desc][off], boxes[desc][off + 1] = val
-                c0, c1, mirror = i0 + qn, Q - 1 - qn, qn >= zskip
-                for desc in (False, True):
-                    do = ((isd or mirror) and wd > 0) if desc else ((not isd) or mirror)
-                    if not do:
-                        continue
-                    col = (c0 if isd else c1) if desc else (c1 if isd else c0)
-                    w = 2 * (wd if desc else wa)
-                    coord0 = 2 * (col * N + (p0 if desc else i0 + q0))
-                    for x in range(8):
-                        seg = boxes[desc][x * w:(x + 1) * w]
-                        assert not np.isnan(seg).any()
-                        assert np.isnan(mem[x, coord0:coord0 + w]).all()
-                        mem[x, coord0:coord0 + w] = seg
-    assert not np.isnan(mem).any()
-    return (mem[:, 0::2] + 1j * mem[:, 1::2]).reshape(nb, N, N).transpose(0, 2, 1)
-
-
-@pytest.mark.parametrize("twoj", [5, 6, 7, 20, 33, 63, 64, 66, 67, 99, 100, 126, 127])
-def test_k3p_quarter_column_boxes_reproduce_wignerD(twoj):
-    rng = np.random.default_rng(1000 + twoj)
-    al, be, ga = rng.uniform(0, 6.3, 8), rng.uniform(0, 3.14, 8), rng.uniform(0, 6.3, 8)
-    got = model_parts(twoj, al, be, ga)
-    ref = o.wignerD_batch(twoj / 2, al, be, ga)
-    assert np.abs(got - ref).max() < 1e-13

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
 SRC = os.path.join(HERE, "csrc", "wd_api.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "wd_k2_col.cuh"), os.path.join(HERE, "csrc", "wd_kernels.cuh"), os.path.join(HERE, "csrc", "wd_k2_dmma.cuh"), os.path.join(HERE, "csrc", "wd_k2_stream.cuh"), os.path.join(HERE, "csrc", "wd_k3_tma.cuh"), os.path.join(HERE, "csrc", "wd_k3_tma_p.cuh"), os.path.join(HERE, "csrc", "wd_rotate.cuh"), os.path.join(ROOT, "include", "wignerd_b200.h")]
+DEPS = [SRC, os.path.join(HERE, "csrc", "wd_k2_col.cuh"), os.path.join(HERE, "csrc", "wd_kernels.cuh"), os.path.join(HERE, "csrc", "wd_k2_dmma.cuh"), os.path.join(HERE, "csrc", "wd_k2_stream.cuh"), os.path.join(HERE, "csrc", "wd_k3_tma.cuh"), os.path.join(HERE, "csrc", "wd_rotate.cuh"), os.path.join(ROOT, "include", "wignerd_b200.h")]
 LIB = os.path.join(HERE, "libwignerd_b200.so")
 
 NVCC_FLAGS = [

@@ -9,7 +9,6 @@
 #include "wd_k2_stream.cuh"
 #include "wd_k2_col.cuh"
 #include "wd_k3_tma.cuh"
-#include "wd_k3_tma_p.cuh"
 #include "wd_rotate.cuh"
 
 #include <algorithm>
@@ -165,7 +164,6 @@ struct wd_handle_s {
     bool attr_set_real[2] = {false, false};
     bool attr_set_col[2][8] = {};
     bool attr_set_k3t[2][8] = {};
-    bool attr_set_k3p[2] = {false, false};
     int *d_pair = nullptr;            // ring of device flags written by k2c_pair_check_kernel (one per call in flight)
     unsigned pair_idx = 0;
     const int *shared_pair_flag = nullptr;   // wd_d_multi: ONE symmetry check of the angle grid (at the tightest tolerance) for all j
@@ -553,70 +551,6 @@ int launch_k3t(wd_handle_t h, const K2Args &a, size_t smem)
     return WD_OK;
 }
 
-// Tensor-store complex-D kernel with three warps per SM sub-partition (k3_tmap_kernel, wd_k3_tma_p.cuh)
-int k3p_slots(wd_handle_t h, const PlanDev &p, size_t *bytes)
-{
-    if (!k3t_shape_ok(p.twoj)) { *bytes = (size_t)1 << 40; return 0; }
-    for (int ns = 3; ns >= 2; --ns) {
-        *bytes = (size_t)k3p_smem_layout(p.Q, p.Kp, p.ldu, ns).total * sizeof(double);
-        if (*bytes <= h->smem_optin) return ns;
-    }
-    return 0;
-}
-bool k3p_fits(wd_handle_t h, const PlanDev &p, const double *out, size_t *bytes)
-{
-    return k3p_slots(h, p, bytes) != 0 && (((uintptr_t)out) & 15) == 0 && encode_tiled_fn() != nullptr;
-}
-
-template <bool HALF>
-cudaError_t launch_k3p_t(wd_handle_t h, const K3PArgs &c, const K3PMaps &tm, int grid, size_t smem)
-{
-    bool &attr_set = h->attr_set_k3p[HALF];
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k3_tmap_kernel<HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    k3_tmap_kernel<HALF><<<grid, K3P_THREADS, smem, h->stream>>>(c, tm);
-    return cudaGetLastError();
-}
-
-int launch_k3p(wd_handle_t h, const K2Args &a)
-{
-    size_t smem = 0;
-    K3PArgs c;
-    c.p = a.p; c.alpha = a.alpha; c.beta = a.beta; c.gamma = a.gamma; c.nb = a.nb;
-    c.flags = a.nostore ? K3T_FLAG_NOSTORE : 0;
-    c.handoff = a.handoff;
-    c.nslots = k3p_slots(h, a.p, &smem);
-    // the output as a 2-d tensor of doubles (see launch_k3t); boxes of 8 angles x a quarter column: ascending / descending, part 0 / 1
-    const int N = a.p.N, Q = a.p.Q;
-    K3PMaps tm;
-    const cuuint64_t dims[2] = {(cuuint64_t)2 * N * N, (cuuint64_t)a.nb};
-    const cuuint64_t strides[1] = {(cuuint64_t)N * N * 16};
-    const cuuint32_t estr[2] = {1, 1};
-    const int upc = (((Q + 15) >> 4) + K3P_GP - 1) / K3P_GP;
-    for (int part = 0; part < 2; ++part) {
-        const K3PBox bx = k3p_box(Q, a.p.zskip, part < upc ? part : 0);
-        for (int t = 0; t < 2; ++t) {
-            const cuuint32_t box[2] = {(cuuint32_t)(2 * (t == 0 ? bx.wa : bx.wd)), (cuuint32_t)K3T_ANG};
-            const CUresult r = encode_tiled_fn()(t == 0 ? &tm.asc[part] : &tm.desc[part], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)a.out, dims, strides,
-                                                 box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) return fail(WD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for 2j = %d, %lld matrices", (int)r, a.p.twoj, a.nb);
-        }
-    }
-    const long long nch = (a.nb + K3T_ANG - 1) / K3T_ANG;
-    const long long G = h->num_sms;
-    long long items = nch;
-    if (nch < G) items = nch * std::max<long long>(1, std::min<long long>(16, G / nch));
-    const int grid = (int)std::min<long long>(items, G);
-    const cudaError_t e = (a.p.twoj & 1) ? launch_k3p_t<true>(h, c, tm, grid, smem) : launch_k3p_t<false>(h, c, tm, grid, smem);
-    h->launches++;
-    CU(e);
-    return WD_OK;
-}
-
 // Streaming DMMA kernel (real d, table too large for shared memory): trig table pass + contraction.
 template <bool HALF>
 int launch_stream(wd_handle_t h, const Plan &cpl, const K2Args &a)
@@ -735,7 +669,7 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
     const bool fits = cplx ? cplx_fits(h, pl.dev, &smem) : real_fits(h, pl.dev, &smem);
     // variants 4 / 5 select the real-d column kernel only: complex D and Equator requests are dispatched as in auto mode
     // variant 7 selects the complex-D tensor-store kernel only: real d is dispatched as in auto mode
-    const int variant = (((cplx || equator) && (h->variant == 4 || h->variant == 5)) || ((!cplx || equator) && (h->variant == 7 || h->variant == 8))) ? 0 : h->variant;
+    const int variant = (((cplx || equator) && (h->variant == 4 || h->variant == 5)) || ((!cplx || equator) && h->variant == 7)) ? 0 : h->variant;
     if (variant == 2 && !fits) return fail(WD_ERR_UNSUPPORTED, "2j = %d does not fit the DMMA kernel (%zu B of shared memory)", pl.dev.twoj, smem);
     // Equator() requests (single matrices, exact zeros of :230-237) take the plain kernel
     if (variant == 3 && !cplx && !equator) return (pl.dev.twoj & 1) ? launch_stream<true>(h, pl, a) : launch_stream<false>(h, pl, a);
@@ -757,11 +691,6 @@ int contract_device(wd_handle_t h, const Plan &pl, const double *alpha, const do
             a.skip_flag = flag;
             return half ? launch_real<true>(h, a, smem) : launch_real<false>(h, a, smem);
         }
-    }
-    if (cplx && !equator && variant == 8) {
-        size_t psm = 0;
-        if (!k3p_fits(h, pl.dev, out, &psm)) return fail(WD_ERR_UNSUPPORTED, "2j = %d does not fit the 12-warp tensor-store kernel (%zu B of shared memory)", pl.dev.twoj, psm);
-        return launch_k3p(h, a);
     }
     if (cplx && !equator && (variant == 0 || variant == 7)) {
         // complex D: the tensor-store kernel (k3_tma_kernel) when its boxes fit in shared memory, else k2_cplx_kernel / streaming
@@ -1373,7 +1302,7 @@ int wd_cache_clear(wd_handle_t h)
 int wd_set_variant(wd_handle_t h, int variant)
 {
     if (!h) return fail(WD_ERR_ASSERT, "null handle");
-    if (variant < 0 || variant > 8) return fail(WD_ERR_ASSERT, "variant must be 0..8");
+    if (variant < 0 || variant > 7) return fail(WD_ERR_ASSERT, "variant must be 0..7");
     if (!h->children.empty()) return for_each_child(h, [variant](wd_handle_t c, int) { return wd_set_variant(c, variant); });
     std::lock_guard<std::mutex> lk(h->mtx);
     h->pairing = variant != 6;                            // 6 = auto without the beta <-> pi - beta pairing of symmetric grids
