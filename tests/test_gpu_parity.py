@@ -504,7 +504,7 @@ def test_tensor_store_kernel_vs_oracle_and_other_kernels(engine, twoj, nb):
     ref = o.wignerD_batch(F(twoj, 2), a, b, g)
     assert np.abs(got[7] - ref).max() < TOL
     assert np.abs(got[7] - got[1]).max() < TOL
-    assert np.abs(got[7] - got[2]).max() < 2e-13
+    assert np.abs(got[7] - got[2]).max() < 4e-13       # k3_tma_kernel makes its phase tables by anchored rotations (<= 6e-14 per factor from one sincos per entry)
     assert np.abs(engine.wignerD_batch(F(twoj, 2), a, b, g) - got[7]).max() == 0.0      # auto mode takes the same kernel
 
 
@@ -526,7 +526,7 @@ def test_tensor_store_kernel_many_items(engine, twoj):
     finally:
         engine.set_variant(0)
     torch.cuda.synchronize()
-    assert float((D7 - D2).abs().max()) < 2e-13
+    assert float((D7 - D2).abs().max()) < 4e-13
     eye = torch.eye(twoj + 1, dtype=D7.dtype, device="cuda")
     assert float((D7.conj().transpose(1, 2) @ D7 - eye).abs().max()) < 1e-12
     pick = np.array([0, 1, 7, 8, 9, 148 * 8 - 1, 148 * 8, nb - 12, nb - 4, nb - 3, nb - 1])

@@ -22,8 +22,8 @@
 // box t-2 must have read its slot before box t is written (cp.async.bulk.wait_group.read 1).
 // Trig and phase tables of item k+1 are made during item k (mbarriers, no CTA barrier), pair hand-off as in k2_col_kernel.
 //
-// Measured at cfg-3 (one B200): 3.24 ms = 4.93 TB/s = 75 % of the measured HBM write roof (k2_cplx_kernel: 3.96 ms); without
-// its tensor stores 3.14 ms, DMMA pipe 59 % (floor 1.94 ms): the SM side binds.  What was tried around it (a third staging
+// Measured at cfg-3 (one B200): 3.19 ms = 5.01 TB/s = 77 % of the measured HBM write roof (k2_cplx_kernel: 3.96 ms); without
+// its tensor stores ~3.1 ms, DMMA pipe 60 % (floor 1.94 ms): the SM side binds.  What was tried around it (a third staging
 // box, 12 warps, software-pipelined epilogue pieces, merged accumulators, release points): DESIGN.md section 4.
 // NW (warps per CTA) is a template parameter because the 12-warp form was measured; the library instantiates NW = 8 only.
 #pragma once
@@ -304,16 +304,29 @@ __global__ void __launch_bounds__(NW * 32, 1) k3_tma_kernel(const K3TArgs a, con
             tc[ang * ldt + kp] = w * cs;
             ts[ang * ldt + kp] = w * sn;
         }
+        // phase tables: runs of 8 consecutive m (or n) per thread -- an exact sincos(fl(m x)) anchor at the run's first entry, then
+        // rotations by x (<= 7 steps: the trig values stay within ~1e-15 of the anchored form; one sincos per entry made the
+        // tables 10 % of a warp's time at cfg-3)
         double *ph = sm + L.ph + bn * L.ph_size;
+        const int nruns = (Q + 7) >> 3;
 #pragma unroll 1
-        for (int idx = tid; idx < 2 * K3T_ANG * Q; idx += (NW * 32)) {
-            const int which = idx / (K3T_ANG * Q), rem2 = idx - which * (K3T_ANG * Q);
-            const int ang = rem2 / Q, q = rem2 - ang * Q;
+        for (int idx = tid; idx < 2 * K3T_ANG * nruns; idx += (NW * 32)) {
+            const int which = idx / (K3T_ANG * nruns), rem2 = idx - which * (K3T_ANG * nruns);
+            const int ang = rem2 / nruns, q0 = 8 * (rem2 - ang * nruns);
             long long b = itn.f0 + ang; if (b >= a.nb) b = a.nb - 1;
-            double sn, cs;
-            sincos(((double)q + mhalf) * (which ? a.gamma[b] : a.alpha[b]), &sn, &cs);
-            ph[((2 * which + 0) * K3T_ANG + ang) * qp + k3t_perm(q)] = cs;
-            ph[((2 * which + 1) * K3T_ANG + ang) * qp + k3t_perm(q)] = sn;
+            const double x = which ? a.gamma[b] : a.alpha[b];
+            double sx, cx1, sn, cs;
+            sincos(x, &sx, &cx1);
+            sincos(((double)q0 + mhalf) * x, &sn, &cs);
+            double *pc = ph + ((2 * which + 0) * K3T_ANG + ang) * qp, *ps = ph + ((2 * which + 1) * K3T_ANG + ang) * qp;
+            const int qe = min(q0 + 8, Q);
+#pragma unroll 1
+            for (int q = q0; q < qe; ++q) {
+                pc[k3t_perm(q)] = cs;
+                ps[k3t_perm(q)] = sn;
+                const double c2 = fma(cs, cx1, -(sn * sx)), s2 = fma(sn, cx1, cs * sx);
+                cs = c2; sn = s2;
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(trig_ready + bn);
