@@ -480,31 +480,25 @@ EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
-constexpr int kK3TWarps = 8;         // two warps per SM sub-partition (12 = three was tried: 168 registers spill, see wd_k3_tma.cuh)
+constexpr int kK3TWarps = 8;         // two warps per SM sub-partition (three were tried)
 bool k3t_fits(wd_handle_t h, const PlanDev &p, const double *out, size_t *bytes)
 {
     *bytes = (size_t)k3t_smem_layout(p.Q, p.Kp, p.ldu, kK3TWarps).total * sizeof(double);
     return k3t_shape_ok(p.twoj) && *bytes <= h->smem_optin && (((uintptr_t)out) & 15) == 0 && encode_tiled_fn() != nullptr;
 }
 
-template <bool HALF, int GC, int NW>
+template <bool HALF, int GC>
 cudaError_t launch_k3t_gc(wd_handle_t h, const K3TArgs &c, const CUtensorMap &ta, const CUtensorMap &td, int grid, size_t smem)
 {
     bool &attr_set = h->attr_set_k3t[HALF][GC];
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k3_tma_kernel<HALF, GC, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
+        cudaError_t e = cudaFuncSetAttribute(k3_tma_kernel<HALF, GC, kK3TWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    k3_tma_kernel<HALF, GC, NW><<<grid, NW * 32, smem, h->stream>>>(c, ta, td);
+    k3_tma_kernel<HALF, GC, kK3TWarps><<<grid, kK3TWarps * 32, smem, h->stream>>>(c, ta, td);
     return cudaGetLastError();
 }
-template <bool HALF, int GC>
-cudaError_t launch_k3t_nw(wd_handle_t h, const K3TArgs &c, const CUtensorMap &ta, const CUtensorMap &td, int grid, size_t smem)
-{
-    return launch_k3t_gc<HALF, GC, kK3TWarps>(h, c, ta, td, grid, smem);
-}
-
 int launch_k3t(wd_handle_t h, const K2Args &a, size_t smem)
 {
     K3TArgs c;
@@ -533,17 +527,17 @@ int launch_k3t(wd_handle_t h, const K2Args &a, size_t smem)
     cudaError_t e = cudaErrorInvalidValue;
     if (a.p.twoj & 1) {
         switch (gc) {
-        case 1: e = launch_k3t_nw<true, 1>(h, c, tm[0], tm[1], grid, smem); break;
-        case 2: e = launch_k3t_nw<true, 2>(h, c, tm[0], tm[1], grid, smem); break;
-        case 3: e = launch_k3t_nw<true, 3>(h, c, tm[0], tm[1], grid, smem); break;
-        case 4: e = launch_k3t_nw<true, 4>(h, c, tm[0], tm[1], grid, smem); break;
+        case 1: e = launch_k3t_gc<true, 1>(h, c, tm[0], tm[1], grid, smem); break;
+        case 2: e = launch_k3t_gc<true, 2>(h, c, tm[0], tm[1], grid, smem); break;
+        case 3: e = launch_k3t_gc<true, 3>(h, c, tm[0], tm[1], grid, smem); break;
+        case 4: e = launch_k3t_gc<true, 4>(h, c, tm[0], tm[1], grid, smem); break;
         }
     } else {
         switch (gc) {
-        case 1: e = launch_k3t_nw<false, 1>(h, c, tm[0], tm[1], grid, smem); break;
-        case 2: e = launch_k3t_nw<false, 2>(h, c, tm[0], tm[1], grid, smem); break;
-        case 3: e = launch_k3t_nw<false, 3>(h, c, tm[0], tm[1], grid, smem); break;
-        case 4: e = launch_k3t_nw<false, 4>(h, c, tm[0], tm[1], grid, smem); break;
+        case 1: e = launch_k3t_gc<false, 1>(h, c, tm[0], tm[1], grid, smem); break;
+        case 2: e = launch_k3t_gc<false, 2>(h, c, tm[0], tm[1], grid, smem); break;
+        case 3: e = launch_k3t_gc<false, 3>(h, c, tm[0], tm[1], grid, smem); break;
+        case 4: e = launch_k3t_gc<false, 4>(h, c, tm[0], tm[1], grid, smem); break;
         }
     }
     h->launches++;
